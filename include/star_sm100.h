@@ -1,0 +1,97 @@
+/* star_sm100.h -- C ABI of libstar_sm100.so (star_b200/csrc), the sm_100a kernel library
+ * behind star_b200's drop-in for the STAR denoising hot path.
+ *
+ * The reference (NJU-PCALab/STAR) has no FFI: every kernel it runs is dispatched by
+ * PyTorch (cuDNN / cuBLAS / xformers).  Each entry point below replaces the library call
+ * made at the cited reference line(s); a maintainer binds them with ctypes (see
+ * INTEGRATION.md) from the module that currently makes that call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (tensor.data_ptr()); fp16 unless stated
+ *   - activations are channels-last token matrices X[rows, C], rows ordered (b, t, h, w)
+ *   - ld* arguments are leading dimensions in ELEMENTS
+ *   - `stream` is a cudaStream_t; all calls are asynchronous on it, allocate nothing and
+ *     keep no state besides the per-process driver entry point resolved by star_init
+ *   - return 0 on success, non-zero on error; star_last_error() gives the message
+ */
+#ifndef STAR_SM100_H
+#define STAR_SM100_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAR_FLAG_GEGLU 1     /* W has 2N rows (value|gate): out = value * gelu_erf(gate)  (unet_v2v.py:496-504) */
+#define STAR_FLAG_SILU_OUT 2  /* out = silu(acc)                                            (unet_v2v.py:1340-1342) */
+
+int star_version(void);
+const char* star_last_error(void);
+/* Resolve cuTensorMapEncodeTiled, opt kernels into >48 KB shared memory.  Fails on non-sm_100 devices. */
+int star_init(int device);
+
+/* nn.Linear / Conv2d 1x1 / Conv1d k=1: out[r, n] = sum_k A[r,k] W[n,k] (+bias[n]) (+rowvec[r/rowvec_div, n])
+ * (+residual[r,n]); replaces F.linear / conv at unet_v2v.py:159-162,:195 (attention projections), :503,:526 (GEGLU
+ * feed-forward), :309,:313 (SpatialTransformer proj), :1046,:1084 (TemporalTransformer Conv1d), :648 (skip 1x1),
+ * :2132 (zero convs), :1341-1342,:628 (time embedding). */
+int star_linear(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
+                long long rowvec_div, const void* residual, long long ldres, void* out, long long ldo,
+                long long rows, int K, int N, int flags, void* stream);
+
+/* Conv2d 3x3 stride 1 pad 1 on X[BT,H,W,Cin]; W9 = weight permuted to [Cout][3][3][Cin]; rowvec = per-clip time
+ * embedding added before the next GroupNorm; replaces cuDNN at unet_v2v.py:612,:639,:553-554,:1552. */
+int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div,
+                    const void* residual, long long ldres, void* out, long long ldo, int BT, int H, int W, int Cin,
+                    int Cout, void* stream);
+/* Downsample: Conv2d 3x3 stride 2 padding (2,1) (unet_v2v.py:709-729).  Ho = (H+1)/2 + 1, Wo = (W-1)/2 + 1.
+ * planes_ws: scratch of star_conv2d_s2_workspace_bytes(). */
+long long star_conv2d_s2_workspace_bytes(int BT, int H, int W, int Cin);
+int star_conv2d_3x3_s2(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
+                       int BT, int H, int W, int Cin, int Cout, void* stream);
+/* Conv3d (3,1,1) pad (1,0,0) over frames on X[B,T,HW,Cin]; W3 = weight permuted to [Cout][3][Cin]
+ * (unet_v2v.py:1209-1220). */
+int star_conv_t3(const void* X, const void* W3, const void* bias, const void* residual, long long ldres, void* out,
+                 long long ldo, int B, int T, long long HW, int Cin, int Cout, void* stream);
+/* Stem convs with Cin = 4 (unet_v2v.py:1353 input conv, :2128 input_hint_block); W9 as above. */
+int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, int BT,
+                       int H, int W, int Cout, void* stream);
+
+/* softmax(Q K^T * scale) V, head_dim 64, heads side by side along the row (column offset h*64); batch b uses rows
+ * [b*Nq,(b+1)*Nq) of Q/O and rows [(b/kv_batch_div)*Nk, ...) of K/V.  Replaces
+ * xformers.ops.memory_efficient_attention at unet_v2v.py:179,:184 for spatial self- and text cross-attention. */
+int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                   long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, void* stream);
+/* Temporal self-attention over T frames per pixel; QKV [B*T*HW, ld] with q|k|v at column 0|Ci|2Ci
+ * (unet_v2v.py:483-489 through :158-195). */
+int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,
+                            int heads, int Ci, float scale, void* stream);
+
+/* GroupNorm(32) (+SiLU): nsamples blocks of rows_per_sample rows share statistics -- one frame for the 4-D norms
+ * (unet_v2v.py:268,:610,:635,:1551), the whole clip for the 5-D norms (:1002,:1210-1219). fp32 statistics. */
+long long star_groupnorm_workspace_bytes(int nsamples, int C);
+int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out, int nsamples,
+                   long long rows_per_sample, int C, float eps, int silu, void* workspace, void* stream);
+/* LayerNorm over C (unet_v2v.py:448-450) with fused LIEM gate: gate_mode 0 none, 1 per-row gate[] (spatial LIEM),
+ * 2 temporal LIEM sigmoid(w0*max + w1*mean) (unet_v2v.py:396-411). */
+int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,
+                   int gate_mode, const void* gate, float w0, float w1, void* stream);
+/* Spatial LIEM gate: channel max/mean -> 7x7 conv (2->1) -> sigmoid (unet_v2v.py:380-394).  w98 = conv1.weight
+ * flattened [2][7][7]; mm_ws = scratch rows*2 fp16; gate = rows fp16. */
+int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* gate, int BT, int H, int W, int C,
+                           void* stream);
+
+/* out[rows, Ca+Cb] = [a | b (+c)]  (torch.cat + control residual, unet_v2v.py:1792); c may be NULL */
+int star_concat_add(const void* a, int Ca, const void* b, const void* c, int Cb, void* out, long long rows,
+                    void* stream);
+int star_add(const void* a, const void* b, void* out, long long n, void* stream);
+/* nearest x2 + crop first/last row (unet_v2v.py:563-564): out [BT, 2H-2, 2W, C] */
+int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, void* stream);
+/* (b,c,f,h,w) fp32 -> tokens fp16 [(b f h w), c]  and back (fp16 -> fp16)  (unet_v2v.py:1772,:1808) */
+int star_nchw5_to_tokens(const void* x_f32, void* out, int B, int C, int F, long long HW, void* stream);
+int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, int F, long long HW, void* stream);
+/* sinusoidal timestep embedding (unet_v2v.py:96-108); t = int64 [B]; out fp16 [B, dim] */
+int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream);
+int star_silu(const void* x, void* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE -- per-kernel references for every op in star_b200/ops.py.
+
+Same signatures as ``star_b200.ops`` but computed with plain torch in fp32 on
+whatever device the inputs live on (CPU in the host-logic tests, CUDA in the
+GPU parity tests), rounding to fp16 only where the CUDA kernel does.  Used
+ (a) by tests/test_kernels_gpu.py as the expected value of each C-ABI call,
+ (b) by tests/test_unet_wiring_cpu.py, which monkeypatches these over
+     ``star_b200.ops`` to validate the host graph (weight repacking, op order,
+     layouts) against the golden vectors without a GPU.
+Never imported by the product.
+"""
+import torch
+import torch.nn.functional as F
+
+HALF = torch.float16
+FLAG_GEGLU = 1
+FLAG_SILU_OUT = 2
+
+
+def _f(t):
+    return None if t is None else t.float()
+
+
+def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, out=None):
+    acc = _f(a) @ _f(w).t()
+    if bias is not None:
+        acc = acc + _f(bias)
+    if flags & FLAG_GEGLU:
+        val, gate = acc.chunk(2, dim=-1)
+        acc = val * F.gelu(gate)
+    if rowvec is not None:
+        idx = torch.arange(a.shape[0], device=a.device) // rowvec_div
+        acc = acc + _f(rowvec)[idx]
+    if residual is not None:
+        acc = acc + _f(residual)
+    if flags & FLAG_SILU_OUT:
+        acc = F.silu(acc)
+    res = acc.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=None):
+    BT, H, W, Cin = x.shape
+    y = F.conv2d(_f(x).permute(0, 3, 1, 2), _f(w9).permute(0, 3, 1, 2), _f(bias), padding=1)
+    y = y.permute(0, 2, 3, 1).reshape(BT * H * W, -1)
+    if rowvec is not None:
+        idx = torch.arange(y.shape[0], device=x.device) // rowvec_div
+        y = y + _f(rowvec)[idx]
+    if residual is not None:
+        y = y + _f(residual)
+    res = y.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def conv2d_3x3_s2(x, w9, bias=None):
+    BT, H, W, Cin = x.shape
+    y = F.conv2d(_f(x).permute(0, 3, 1, 2), _f(w9).permute(0, 3, 1, 2), _f(bias), stride=2, padding=(2, 1))
+    Ho, Wo = y.shape[2], y.shape[3]
+    return y.permute(0, 2, 3, 1).reshape(BT * Ho * Wo, -1).to(HALF), Ho, Wo
+
+
+def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
+    Cin = x.shape[1]
+    x5 = _f(x).reshape(B, T, HW, Cin).permute(0, 3, 1, 2)            # b c t hw
+    w = _f(w3).permute(0, 2, 1)[..., None]                          # cout cin 3 1
+    y = F.conv2d(x5, w, _f(bias), padding=(1, 0))
+    y = y.permute(0, 2, 3, 1).reshape(B * T * HW, -1)
+    if residual is not None:
+        y = y + _f(residual)
+    res = y.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def conv2d_3x3_c4(x, w9, bias=None, residual=None):
+    BT, H, W, C = x.shape
+    y = F.conv2d(_f(x).permute(0, 3, 1, 2), _f(w9).permute(0, 3, 1, 2), _f(bias), padding=1)
+    y = y.permute(0, 2, 3, 1).reshape(BT * H * W, -1)
+    if residual is not None:
+        y = y.to(HALF).float() + _f(residual)
+    return y.to(HALF)
+
+
+def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=None):
+    d = 64
+    qf = _f(q)[:, :heads * d].reshape(batch, Nq, heads, d).permute(0, 2, 1, 3)
+    kvb = (batch + kv_batch_div - 1) // kv_batch_div
+    kf = _f(k)[:, :heads * d].reshape(kvb, Nk, heads, d).permute(0, 2, 1, 3)
+    vf = _f(v)[:, :heads * d].reshape(kvb, Nk, heads, d).permute(0, 2, 1, 3)
+    idx = torch.arange(batch, device=q.device) // kv_batch_div
+    o = F.scaled_dot_product_attention(qf, kf[idx], vf[idx], scale=scale)
+    res = o.permute(0, 2, 1, 3).reshape(batch * Nq, heads * d).to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
+    d = 64
+    x = _f(qkv).reshape(B, T, HW, -1)
+
+    def split(t):
+        return t.reshape(B, T, HW, heads, d).permute(0, 2, 3, 1, 4)     # b hw h t d
+
+    q, k, v = split(x[..., :Ci]), split(x[..., Ci:2 * Ci]), split(x[..., 2 * Ci:3 * Ci])
+    o = F.scaled_dot_product_attention(q, k, v, scale=scale)
+    return o.permute(0, 3, 1, 2, 4).reshape(B * T * HW, Ci).to(HALF)
+
+
+def groupnorm(x, gamma, beta, nsamples, eps, silu):
+    rows, C = x.shape
+    xs = _f(x).reshape(nsamples, rows // nsamples, C).permute(0, 2, 1)          # n c r
+    y = F.group_norm(xs, 32, _f(gamma), _f(beta), eps)
+    if silu:
+        y = F.silu(y)
+    return y.permute(0, 2, 1).reshape(rows, C).to(HALF)
+
+
+def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
+    xf = _f(x)
+    if gate_mode == 1:
+        xf = (xf * _f(gate)[:, None]).to(HALF).float()
+    elif gate_mode == 2:
+        mx = xf.max(dim=-1, keepdim=True)[0]
+        mean = xf.mean(dim=-1, keepdim=True).to(HALF).float()
+        lin = (w0 * mx + w1 * mean).to(HALF).float()
+        g = torch.sigmoid(lin).to(HALF).float()
+        xf = (xf * g).to(HALF).float()
+    return F.layer_norm(xf, (x.shape[1],), _f(gamma), _f(beta), eps).to(HALF)
+
+
+def liem_spatial_gate(x, w98, BT, H, W):
+    xf = _f(x).reshape(BT, H, W, -1)
+    mx = xf.max(dim=-1)[0]
+    mean = xf.mean(dim=-1)
+    mm = torch.stack([mx, mean], dim=1).to(HALF).float()                       # bt 2 h w
+    conv = F.conv2d(mm, _f(w98).reshape(1, 2, 7, 7), padding=3).to(HALF).float()
+    return torch.sigmoid(conv).reshape(-1).to(HALF)
+
+
+def concat_add(a, b, c=None):
+    bb = b if c is None else (_f(b) + _f(c)).to(HALF)
+    return torch.cat([a, bb], dim=1)
+
+
+def add(a, b):
+    return (_f(a) + _f(b)).to(HALF)
+
+
+def upsample2x_crop(x, BT, H, W):
+    C = x.shape[1]
+    x4 = x.reshape(BT, H, W, C)
+    up = x4.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)[:, 1:-1]
+    return up.reshape(-1, C).contiguous()
+
+
+def nchw5_to_tokens(x):
+    B, C, Fr, H, W = x.shape
+    return x.float().permute(0, 2, 3, 4, 1).reshape(B * Fr * H * W, C).to(HALF)
+
+
+def tokens_to_nchw5(x, B, C, Fr, H, W):
+    return x[:, :C].reshape(B, Fr, H, W, C).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def sinusoidal(t, dim):
+    half = dim // 2
+    tf = t.float()
+    freqs = torch.pow(10000, -torch.arange(half, device=t.device).float().div(half))
+    s = torch.outer(tf, freqs)
+    return torch.cat([torch.cos(s), torch.sin(s)], dim=1).to(HALF)
+
+
+def silu(x):
+    return F.silu(_f(x)).to(HALF)

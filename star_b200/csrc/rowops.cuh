@@ -1,0 +1,513 @@
+// star_b200 / csrc / rowops.cuh
+// HBM-bound kernels of the STAR UNet on the channels-last token matrix X[R, C] (fp16,
+// rows ordered (b, t, h, w)): layout conversion, GroupNorm (4-D per-frame and 5-D
+// per-clip statistics), LayerNorm with fused LIEM gates, spatial LIEM gate, temporal
+// self-attention over T, channel concat, nearest-upsample, stride-2 parity split, and the
+// 4-channel stem convolution.  All global accesses are 128-bit along C.
+#pragma once
+#include "common.cuh"
+
+namespace star {
+
+STAR_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+STAR_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+STAR_DEVINL void unpack8(const uint4& u, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+STAR_DEVINL uint4 pack8(const float* f) {
+    uint4 u;
+    u.x = pack_half2(f[0], f[1]);
+    u.y = pack_half2(f[2], f[3]);
+    u.z = pack_half2(f[4], f[5]);
+    u.w = pack_half2(f[6], f[7]);
+    return u;
+}
+
+// ------------------------------------------------------------------ layout conversion
+// (b, c, f, h, w) fp32  ->  tokens [(b f h w), c] fp16      (unet_v2v.py:1772 rearrange + autocast cast)
+__global__ void nchw5_to_tokens_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int C, int F,
+                                       long long HW) {
+    const long long n = (long long)B * F * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long hw = i % HW;
+        const long long bf = i / HW;
+        const int f = (int)(bf % F), b = (int)(bf / F);
+        for (int c = 0; c < C; ++c)
+            out[i * C + c] = __float2half_rn(x[(((long long)b * C + c) * F + f) * HW + hw]);
+    }
+}
+// tokens [(b f h w), c] fp16 -> (b, c, f, h, w) fp16         (unet_v2v.py:1808)
+__global__ void tokens_to_nchw5_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, int B,
+                                       int C, int F, long long HW) {
+    const long long n = (long long)B * F * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long hw = i % HW;
+        const long long bf = i / HW;
+        const int f = (int)(bf % F), b = (int)(bf / F);
+        for (int c = 0; c < C; ++c) out[(((long long)b * C + c) * F + f) * HW + hw] = x[i * ldx + c];
+    }
+}
+
+// ------------------------------------------------------------------ stem conv: 3x3, Cin = 4 (unet_v2v.py:1353, :2128)
+// X [BT, H, W, 4] fp16; Wt [Cout][9*4] (tap-major, then cin); out [BT*H*W, Cout] (+bias, +residual)
+__global__ void conv3x3_c4_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
+                                  const __half* __restrict__ bias, const __half* __restrict__ residual,
+                                  __half* __restrict__ out, int BT, int H, int W, int Cout) {
+    extern __shared__ __half w_s[];      // [36][Cout]
+    const int groups = Cout / 8;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 36 * Cout; i += blockDim.x * blockDim.y) {
+        const int k = i / Cout, n = i % Cout;
+        w_s[i] = wt[n * 36 + k];
+    }
+    __syncthreads();
+    const long long npix = (long long)BT * H * W;
+    const long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    if (pix >= npix || threadIdx.x >= groups) return;
+    const int w0 = (int)(pix % W);
+    const int h0 = (int)((pix / W) % H);
+    const long long bt = pix / ((long long)W * H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __half2float(bias[threadIdx.x * 8 + j]) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hh = h0 + r - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int ww = w0 + s - 1;
+            if (ww < 0 || ww >= W) continue;
+            const uint2 xv = *reinterpret_cast<const uint2*>(x + ((bt * H + hh) * W + ww) * 4);
+            const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+            const float2 x01 = __half22float2(xh[0]), x23 = __half22float2(xh[1]);
+            const float xi[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 wv = *reinterpret_cast<const uint4*>(w_s + ((r * 3 + s) * 4 + c) * Cout + threadIdx.x * 8);
+                float wf[8];
+                unpack8(wv, wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xi[c], wf[j], acc[j]);
+            }
+        }
+    }
+    if (residual) {
+        float rf[8];
+        unpack8(*reinterpret_cast<const uint4*>(residual + pix * Cout + threadIdx.x * 8), rf);
+        // reference adds the hint feature to the fp16 conv output (unet_v2v.py:2193): round first
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __half2float(__float2half_rn(acc[j])) + rf[j];
+    }
+    *reinterpret_cast<uint4*>(out + pix * Cout + threadIdx.x * 8) = pack8(acc);
+}
+
+// ------------------------------------------------------------------ GroupNorm (32 groups)
+// stats: per (sample, group) sum / sum of squares in double.  A "sample" is rows_per_sample
+// consecutive rows: one frame for the 4-D GroupNorms (unet_v2v.py:610, :635, :268) and the whole
+// clip (all frames) for the 5-D ones (unet_v2v.py:1002 on b c f h w, :1210-1219).
+constexpr int GN_THREADS = 512;
+constexpr int GN_SLAB = 256;     // rows per CTA
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __half* __restrict__ x, double* __restrict__ stats, long long rows_per_sample, int C) {
+    extern __shared__ float red[];            // [lanes][C][2]
+    const int O = C / 8;
+    const int lanes = max(1, GN_THREADS / O);
+    const int sample = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * GN_SLAB;
+    const long long r1 = min(rows_per_sample, r0 + GN_SLAB);
+    const __half* xs = x + (long long)sample * rows_per_sample * C;
+    for (int obase = 0; obase < O; obase += GN_THREADS) {      // only loops when C/8 > 512
+        const int tid = threadIdx.x;
+        int oc, ln;
+        if (O >= GN_THREADS) { oc = obase + tid; ln = 0; }
+        else { oc = tid % O; ln = tid / O; }
+        float s[8], ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+        const bool active = (oc < O) && (ln < lanes);
+        if (active) {
+            for (long long r = r0 + ln; r < r1; r += lanes) {
+                float f[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(xs + r * C + oc * 8)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[((size_t)ln * C + oc * 8 + j) * 2] = s[j];
+                red[((size_t)ln * C + oc * 8 + j) * 2 + 1] = ss[j];
+            }
+        }
+    }
+    __syncthreads();
+    // 32 groups: warp g reduces group g's (lanes x C/32 channels) partials
+    const int cg = C / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < 32; g += GN_THREADS / 32) {
+        float s = 0.f, ss = 0.f;
+        for (int i = lane; i < lanes * cg; i += 32) {
+            const int ln = i / cg, c = g * cg + i % cg;
+            s += red[((size_t)ln * C + c) * 2];
+            ss += red[((size_t)ln * C + c) * 2 + 1];
+        }
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            atomicAdd(&stats[((long long)sample * 32 + g) * 2], (double)s);
+            atomicAdd(&stats[((long long)sample * 32 + g) * 2 + 1], (double)ss);
+        }
+    }
+}
+
+// per (sample, channel) affine: y = x * a + b,  a = gamma * rstd, b = beta - mean * a
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const __half* __restrict__ gamma,
+                                   const __half* __restrict__ beta, float* __restrict__ ab, long long rows_per_sample,
+                                   int C, float eps) {
+    const int sample = blockIdx.x;
+    const int cg = C / 32;
+    const double cnt = (double)rows_per_sample * cg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cg;
+        const double mean = stats[((long long)sample * 32 + g) * 2] / cnt;
+        double var = stats[((long long)sample * 32 + g) * 2 + 1] / cnt - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float a = __half2float(gamma[c]) * rstd;
+        ab[((long long)sample * C + c) * 2] = a;
+        ab[((long long)sample * C + c) * 2 + 1] = __half2float(beta[c]) - (float)mean * a;
+    }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ out,
+                                long long rows_per_sample, long long total_rows, int C, int silu) {
+    const int O = C / 8;
+    const long long n = total_rows * O;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / O;
+        const int oc = (int)(i % O);
+        const long long sample = row / rows_per_sample;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+        const float4* abp = reinterpret_cast<const float4*>(ab + (sample * C + oc * 8) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 q = __ldg(abp + j);
+            float y0 = fmaf(f[2 * j], q.x, q.y), y1 = fmaf(f[2 * j + 1], q.z, q.w);
+            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            f[2 * j] = y0;
+            f[2 * j + 1] = y1;
+        }
+        *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm over C with fused LIEM gate
+// gate_mode 0: y = LN(x)
+// gate_mode 1: y = LN(x * gate[row])            spatial LIEM, gate from liem_spatial_gate (unet_v2v.py:468-473)
+// gate_mode 2: y = LN(x * sigmoid(w0*max_c(x) + w1*mean_c(x)))   temporal LIEM (unet_v2v.py:402-411, :481-487)
+// One warp per row; the row lives in registers (C <= 1280 -> <= 5 x 8 values per lane).
+constexpr int LN_MAX_OCT = 5;
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                 __half* __restrict__ out, long long rows, int C, float eps, int gate_mode,
+                 const __half* __restrict__ gate, float w0, float w1) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int O = C / 8;
+    float v[LN_MAX_OCT][8];
+    float s = 0.f, mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_OCT; ++i) {
+        const int oc = lane + 32 * i;
+        if (oc < O) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s += v[i][j]; mx = fmaxf(mx, v[i][j]); }
+        }
+    }
+    if (gate_mode != 0) {
+        float g;
+        if (gate_mode == 1) {
+            g = __half2float(gate[row]);
+        } else {
+            s = warp_sum(s);
+            mx = warp_max(mx);
+            // reference computes max / mean / Linear(2->1) / sigmoid in fp16 (autocast keeps input dtype)
+            const float mean_h = __half2float(__float2half_rn(s / (float)C));
+            const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
+            g = __half2float(__float2half_rn(sigmoid_f(lin)));
+        }
+        s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_OCT; ++i) {
+            const int oc = lane + 32 * i;
+            if (oc < O) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[i][j] = __half2float(__float2half_rn(v[i][j] * g));     // fp16 product, as the reference
+                    s += v[i][j];
+                }
+            }
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_OCT; ++i) {
+        const int oc = lane + 32 * i;
+        if (oc < O) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var = fmaf(d, d, var); }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_OCT; ++i) {
+        const int oc = lane + 32 * i;
+        if (oc < O) {
+            float gm[8], bt[8], y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + oc * 8)), gm);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(beta + oc * 8)), bt);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+            *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ spatial LIEM gate (unet_v2v.py:380-394)
+// step 1: per token channel-max and channel-mean -> mm[R][2] fp16
+__global__ void __launch_bounds__(256)
+liem_reduce_kernel(const __half* __restrict__ x, __half* __restrict__ mm, long long rows, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int O = C / 8;
+    float s = 0.f, mx = -INFINITY;
+    for (int oc = lane; oc < O; oc += 32) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s += f[j]; mx = fmaxf(mx, f[j]); }
+    }
+    s = warp_sum(s);
+    mx = warp_max(mx);
+    if (lane == 0) {
+        __half2 h = __floats2half2_rn(mx, s / (float)C);
+        *reinterpret_cast<__half2*>(mm + row * 2) = h;
+    }
+}
+// step 2: 7x7 conv (2 -> 1, pad 3, no bias) + sigmoid -> gate[R] fp16.  wt = conv1.weight[0] as [2][7][7]
+__global__ void liem_conv7_kernel(const __half* __restrict__ mm, const __half* __restrict__ wt, __half* __restrict__ gate,
+                                  int BT, int H, int W) {
+    __shared__ float w_s[98];
+    if (threadIdx.x < 98) w_s[threadIdx.x] = __half2float(wt[threadIdx.x]);
+    __syncthreads();
+    const long long n = (long long)BT * H * W;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int w0 = (int)(i % W), h0 = (int)((i / W) % H);
+    const long long bt = i / ((long long)W * H);
+    float acc = 0.f;
+    for (int r = 0; r < 7; ++r) {
+        const int hh = h0 + r - 3;
+        if (hh < 0 || hh >= H) continue;
+        for (int s = 0; s < 7; ++s) {
+            const int ww = w0 + s - 3;
+            if (ww < 0 || ww >= W) continue;
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(mm + ((bt * H + hh) * W + ww) * 2));
+            acc = fmaf(v.x, w_s[r * 7 + s], acc);
+            acc = fmaf(v.y, w_s[49 + r * 7 + s], acc);
+        }
+    }
+    const float a = __half2float(__float2half_rn(acc));      // fp16 conv output in the reference
+    gate[i] = __float2half_rn(sigmoid_f(a));
+}
+
+// ------------------------------------------------------------------ temporal self-attention (unet_v2v.py:483-489)
+// qkv [R, ld] with q | k | v at column offsets 0 | Ci | 2Ci, rows ordered (b, t, p); one warp per (b, p, head),
+// lane = query frame; K/V of the T frames staged in smem; online softmax in fp32.
+constexpr int TA_WARPS = 4;
+constexpr int TA_MAXT = 64;
+__global__ void __launch_bounds__(TA_WARPS * 32)
+temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int B,
+                     int T, long long HW, int heads, int Ci, float scale) {
+    extern __shared__ uint4 ta_smem[];                // per warp: K [T][8] uint4, V [T][8] uint4
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * TA_WARPS + warp;      // over (b, p, head), head fastest
+    const long long nitems = (long long)B * HW * heads;
+    if (item >= nitems) return;
+    const int head = (int)(item % heads);
+    const long long p = (item / heads) % HW;
+    const int b = (int)(item / (heads * HW));
+    uint4* ks = ta_smem + (size_t)warp * 2 * T * 8;
+    uint4* vs = ks + T * 8;
+    const long long row0 = (long long)b * T * HW + p;            // row of frame 0
+    for (int i = lane; i < T * 8; i += 32) {
+        const int t = i >> 3, ch = i & 7;
+        const __half* base = qkv + (row0 + (long long)t * HW) * ld + head * 64 + ch * 8;
+        ks[i] = __ldg(reinterpret_cast<const uint4*>(base + Ci));
+        vs[i] = __ldg(reinterpret_cast<const uint4*>(base + 2 * Ci));
+    }
+    __syncwarp();
+    const float sl2 = scale * 1.4426950408889634f;
+    for (int tq = lane; tq < T; tq += 32) {
+        uint4 qv[8];
+        const __half* qb = qkv + (row0 + (long long)tq * HW) * ld + head * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qv[c] = __ldg(reinterpret_cast<const uint4*>(qb + c * 8));
+        float o[64];
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o[d] = 0.f;
+        float m = -INFINITY, l = 0.f;
+        for (int s = 0; s < T; ++s) {
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 kk = ks[s * 8 + c];
+                const __half2* qh = reinterpret_cast<const __half2*>(&qv[c]);
+                const __half2* kh = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a = __half22float2(qh[e]), bb = __half22float2(kh[e]);
+                    dot = fmaf(a.x, bb.x, dot);
+                    dot = fmaf(a.y, bb.y, dot);
+                }
+            }
+            const float sc = dot * sl2;
+            const float m_new = fmaxf(m, sc);
+            const float alpha = exp2f(m - m_new);
+            const float pr = exp2f(sc - m_new);
+            l = l * alpha + pr;
+            m = m_new;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 vv = vs[s * 8 + c];
+                const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a = __half22float2(vh[e]);
+                    o[c * 8 + e * 2] = fmaf(o[c * 8 + e * 2], alpha, pr * a.x);
+                    o[c * 8 + e * 2 + 1] = fmaf(o[c * 8 + e * 2 + 1], alpha, pr * a.y);
+                }
+            }
+        }
+        const float inv = 1.f / l;
+        __half* ob = out + (row0 + (long long)tq * HW) * ldo + head * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = o[c * 8 + j] * inv;
+            *reinterpret_cast<uint4*>(ob + c * 8) = pack8(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ elementwise / copies
+// out[R, Ca+Cb] = [ a | b (+ c) ]        decoder skip concat with the control residual (unet_v2v.py:1792)
+__global__ void concat_add_kernel(const __half* __restrict__ a, int Ca, const __half* __restrict__ b,
+                                  const __half* __restrict__ c, int Cb, __half* __restrict__ out, long long rows) {
+    const int Oa = Ca / 8, Ob = Cb / 8, O = Oa + Ob;
+    const long long n = rows * O;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / O;
+        const int oc = (int)(i % O);
+        uint4 v;
+        if (oc < Oa) {
+            v = __ldg(reinterpret_cast<const uint4*>(a + row * Ca + oc * 8));
+        } else {
+            v = __ldg(reinterpret_cast<const uint4*>(b + row * Cb + (oc - Oa) * 8));
+            if (c) {
+                float f[8], g[8];
+                unpack8(v, f);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * Cb + (oc - Oa) * 8)), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += g[j];
+                v = pack8(f);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + row * (long long)(Ca + Cb) + oc * 8) = v;
+    }
+}
+// out = a + b (fp16), n8 = number of 8-element groups
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
+                           long long n8) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float f[8], g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += g[j];
+        reinterpret_cast<uint4*>(out)[i] = pack8(f);
+    }
+}
+// nearest x2 upsample then drop the first and last row (unet_v2v.py:563-564): out H' = 2H-2, W' = 2W
+__global__ void upsample2x_crop_kernel(const __half* __restrict__ x, __half* __restrict__ out, int BT, int H, int W,
+                                       int C) {
+    const int O = C / 8, Ho = 2 * H - 2, Wo = 2 * W;
+    const long long n = (long long)BT * Ho * Wo * O;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int oc = (int)(i % O);
+        long long t = i / O;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho);
+        const long long bt = t / Ho;
+        const int ih = (oh + 1) >> 1, iw = ow >> 1;
+        reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(x + ((bt * H + ih) * W + iw) * C + oc * 8));
+    }
+}
+// stride-2 conv input split (unet_v2v.py:709: stride 2, padding (2,1)):
+// planes[bt][pq][i][j][:] = Xpad[2i + p][2j + q],  Xpad = X zero-padded by 2 rows / 1 column on each side,
+// pq = 2p + q, plane extent (Ho+1, Wo+1) with Ho = (H+1)/2 + 1... computed by the host.
+__global__ void s2_split_kernel(const __half* __restrict__ x, __half* __restrict__ planes, int BT, int H, int W, int C,
+                                int H2, int W2) {
+    const int O = C / 8;
+    const long long n = (long long)BT * 4 * H2 * W2 * O;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int oc = (int)(idx % O);
+        long long t = idx / O;
+        const int j = (int)(t % W2); t /= W2;
+        const int i = (int)(t % H2); t /= H2;
+        const int pq = (int)(t % 4);
+        const long long bt = t / 4;
+        const int ih = 2 * i + (pq >> 1) - 2, iw = 2 * j + (pq & 1) - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = __ldg(reinterpret_cast<const uint4*>(x + ((bt * H + ih) * W + iw) * C + oc * 8));
+        reinterpret_cast<uint4*>(planes)[idx] = v;
+    }
+}
+// sinusoidal timestep embedding cos || sin (unet_v2v.py:96-108) -> fp16 [B, dim]
+__global__ void sinusoidal_kernel(const long long* __restrict__ t, __half* __restrict__ out, int B, int dim) {
+    const int half_d = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half_d) return;
+    const int b = i / half_d, k = i % half_d;
+    const float freq = powf(10000.f, -(float)k / (float)half_d);
+    const float a = (float)t[b] * freq;
+    out[b * dim + k] = __float2half_rn(cosf(a));
+    out[b * dim + half_d + k] = __float2half_rn(sinf(a));
+}
+__global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(silu_f(__half2float(x[i])));
+}
+
+}  // namespace star

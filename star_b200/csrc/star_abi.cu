@@ -1,0 +1,455 @@
+// star_b200 / csrc / star_abi.cu -- host side of libstar_sm100.so (C ABI in include/star_sm100.h)
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/star_sm100.h"
+#include "attn.cuh"
+#include "rowops.cuh"
+#include "tapgemm.cuh"
+
+using namespace star;
+
+namespace {
+
+thread_local std::string g_err;
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_num_sms = 148;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define STAR_CHECK_INIT() \
+    if (!g_encode) return fail("star_init() has not been called (or failed)")
+#define STAR_CUDA(x)                                                                        \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) return fail("%s failed: %s", #x, cudaGetErrorString(e_));    \
+    } while (0)
+#define STAR_LAUNCH_CHECK(name)                                                             \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess) return fail("launch %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// rank-`rank` fp16 tensor map, dims[0] innermost (contiguous), strides in ELEMENTS for dims 1..rank-1
+int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+              const unsigned long long* strides_elems, const unsigned* box) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) {
+            gstr[i - 1] = strides_elems[i] * 2ull;
+            if (gstr[i - 1] % 16) return fail("tensor map stride %llu B of dim %d is not a multiple of 16", (unsigned long long)gstr[i - 1], i);
+        }
+        if (box[i] == 0 || box[i] > 256) return fail("tensor map box[%d]=%u out of range", i, box[i]);
+    }
+    if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+inline int grid_for(long long n, int block, int cap_mult = 32) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max(1ll, std::min(g, (long long)g_num_sms * cap_mult));
+}
+
+// ------------------------------------------------------------------ tap-GEMM launcher
+struct TapDesc {
+    const void* A;
+    unsigned long long adim[5];      // (C, n1..n4) of the input view
+    unsigned long long astr[5];      // element strides of dims 1..4 (astr[0] unused)
+    int on[4];                       // output extents
+    int box[4];
+    int ntaps;
+    int tap[TG_MAX_TAPS][4];
+    int K, N, flags;
+    const void *W, *bias, *rowvec, *residual;
+    long long rowvec_div, ldres, ldo;
+    void* out;
+};
+
+template <int BN>
+int launch_tapgemm_bn(const TapDesc& d, cudaStream_t st) {
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    long long m_tiles = 1;
+    int box_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.on[i] = d.on[i];
+        p.box[i] = d.box[i];
+        p.tiles[i] = (d.on[i] + d.box[i] - 1) / d.box[i];
+        m_tiles *= p.tiles[i];
+        box_rows *= d.box[i];
+    }
+    if (box_rows > TG_BM) return fail("tapgemm: box has %d rows (> %d)", box_rows, TG_BM);
+    p.box_rows = box_rows;
+    p.ntaps = d.ntaps;
+    memcpy(p.tap, d.tap, sizeof(p.tap));
+    p.K = d.K;
+    p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
+    p.N = d.N;
+    p.flags = d.flags;
+    p.bias = (const __half*)d.bias;
+    p.rowvec = (const __half*)d.rowvec;
+    p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
+    p.residual = (const __half*)d.residual;
+    p.res_ld = d.ldres;
+    p.out = (__half*)d.out;
+    p.out_ld = d.ldo;
+    const bool geglu = d.flags & TG_GEGLU;
+    if (geglu && BN != 128) return fail("tapgemm: GEGLU requires BN=128");
+    if (geglu && (d.N % 64)) return fail("tapgemm: GEGLU requires N %% 64 == 0 (N=%d)", d.N);
+    if (m_tiles > 65535) return fail("tapgemm: %lld M tiles exceed grid.y", m_tiles);
+
+    CUtensorMap ta, tw;
+    unsigned abox[5] = {TG_BK, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
+    if (make_tmap(&ta, d.A, 5, d.adim, d.astr, abox)) return 1;
+    const unsigned long long wrows = geglu ? 2ull * d.N : (unsigned long long)d.N;
+    unsigned long long wdim[2] = {(unsigned long long)d.ntaps * d.K, wrows};
+    unsigned long long wstr[2] = {1, (unsigned long long)d.ntaps * d.K};
+    unsigned wbox[2] = {TG_BK, (unsigned)(geglu ? BN / 2 : BN)};
+    if (make_tmap(&tw, d.W, 2, wdim, wstr, wbox)) return 1;
+
+    const int n_per_tile = geglu ? BN / 2 : BN;
+    dim3 grid((d.N + n_per_tile - 1) / n_per_tile, (unsigned)m_tiles, 1);
+    tapgemm_kernel<BN><<<grid, TG_THREADS, TapGemmSmem<BN>::TOTAL, st>>>(ta, tw, p);
+    STAR_LAUNCH_CHECK("tapgemm");
+    return 0;
+}
+
+int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
+    const bool geglu = d.flags & TG_GEGLU;
+    if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm_bn<160>(d, st);
+    return launch_tapgemm_bn<128>(d, st);
+}
+
+void best_box_2d(int H, int W, int* th, int* tw) {
+    long long best = -1;
+    for (int w = 1; w <= std::min(W, 128); ++w) {
+        int h = std::min(H, 128 / w);
+        if (h < 1) continue;
+        long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h);
+        if (best < 0 || tiles < best || (tiles == best && w > *tw)) {
+            best = tiles;
+            *th = h;
+            *tw = w;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int star_version(void) { return 100; }
+const char* star_last_error(void) { return g_err.c_str(); }
+
+int star_init(int device) {
+    STAR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    STAR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("libstar_sm100 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
+    g_num_sms = prop.multiProcessorCount;
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        STAR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<128>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<160>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TA_WARPS * 2 * TA_MAXT * 128));
+    return 0;
+}
+
+int star_linear(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
+                long long rowvec_div, const void* residual, long long ldres, void* out, long long ldo,
+                long long rows, int K, int N, int flags, void* stream) {
+    STAR_CHECK_INIT();
+    if (rows <= 0) return 0;
+    if (K % 8 || lda % 8) return fail("star_linear: K and lda must be multiples of 8 (K=%d lda=%lld)", K, lda);
+    TapDesc d;
+    memset(&d, 0, sizeof(d));
+    d.A = A;
+    d.adim[0] = K; d.adim[1] = rows; d.adim[2] = d.adim[3] = d.adim[4] = 1;
+    d.astr[1] = lda; d.astr[2] = d.astr[3] = d.astr[4] = (unsigned long long)lda * rows;
+    d.on[0] = (int)rows; d.on[1] = d.on[2] = d.on[3] = 1;
+    d.box[0] = TG_BM; d.box[1] = d.box[2] = d.box[3] = 1;
+    if (rows > 0x7fffffffll) return fail("star_linear: too many rows");
+    d.ntaps = 1;
+    d.K = K; d.N = N; d.flags = flags;
+    d.W = W; d.bias = bias; d.rowvec = rowvec; d.rowvec_div = rowvec_div; d.residual = residual; d.ldres = ldres;
+    d.out = out; d.ldo = ldo;
+    return launch_tapgemm(d, (cudaStream_t)stream);
+}
+
+int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div,
+                    const void* residual, long long ldres, void* out, long long ldo, int BT, int H, int W, int Cin,
+                    int Cout, void* stream) {
+    STAR_CHECK_INIT();
+    if (Cin % 8) return fail("star_conv2d_3x3: Cin must be a multiple of 8");
+    TapDesc d;
+    memset(&d, 0, sizeof(d));
+    d.A = X;
+    d.adim[0] = Cin; d.adim[1] = W; d.adim[2] = H; d.adim[3] = BT; d.adim[4] = 1;
+    d.astr[1] = Cin; d.astr[2] = (unsigned long long)Cin * W; d.astr[3] = (unsigned long long)Cin * W * H;
+    d.astr[4] = (unsigned long long)Cin * W * H * BT;
+    d.on[0] = W; d.on[1] = H; d.on[2] = BT; d.on[3] = 1;
+    int th = 1, tw = 1;
+    best_box_2d(H, W, &th, &tw);
+    d.box[0] = tw; d.box[1] = th; d.box[2] = std::max(1, std::min(BT, TG_BM / (tw * th))); d.box[3] = 1;
+    d.ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            d.tap[r * 3 + s][0] = s - 1;
+            d.tap[r * 3 + s][1] = r - 1;
+        }
+    d.K = Cin; d.N = Cout;
+    d.W = W9; d.bias = bias; d.rowvec = rowvec; d.rowvec_div = rowvec_div; d.residual = residual; d.ldres = ldres;
+    d.out = out; d.ldo = ldo;
+    return launch_tapgemm(d, (cudaStream_t)stream);
+}
+
+long long star_conv2d_s2_workspace_bytes(int BT, int H, int W, int Cin) {
+    const long long Ho = (H + 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    return (long long)BT * 4 * (Ho + 1) * (Wo + 1) * Cin * 2;
+}
+
+int star_conv2d_3x3_s2(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
+                       int BT, int H, int W, int Cin, int Cout, void* stream) {
+    STAR_CHECK_INIT();
+    if (Cin % 8) return fail("star_conv2d_3x3_s2: Cin must be a multiple of 8");
+    const int Ho = (H + 1) / 2 + 1, Wo = (W - 1) / 2 + 1, H2 = Ho + 1, W2 = Wo + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)BT * 4 * H2 * W2 * (Cin / 8);
+    s2_split_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)X, (__half*)planes_ws, BT, H, W, Cin, H2, W2);
+    STAR_LAUNCH_CHECK("s2_split");
+    TapDesc d;
+    memset(&d, 0, sizeof(d));
+    d.A = planes_ws;
+    d.adim[0] = Cin; d.adim[1] = W2; d.adim[2] = H2; d.adim[3] = 4; d.adim[4] = BT;
+    d.astr[1] = Cin; d.astr[2] = (unsigned long long)Cin * W2; d.astr[3] = (unsigned long long)Cin * W2 * H2;
+    d.astr[4] = (unsigned long long)Cin * W2 * H2 * 4;
+    d.on[0] = Wo; d.on[1] = Ho; d.on[2] = 1; d.on[3] = BT;
+    int th = 1, tw = 1;
+    best_box_2d(Ho, Wo, &th, &tw);
+    d.box[0] = tw; d.box[1] = th; d.box[2] = 1; d.box[3] = 1;
+    d.ntaps = 9;
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            d.tap[r * 3 + s][0] = s >> 1;
+            d.tap[r * 3 + s][1] = r >> 1;
+            d.tap[r * 3 + s][2] = (r & 1) * 2 + (s & 1);
+        }
+    d.K = Cin; d.N = Cout;
+    d.W = W9; d.bias = bias;
+    d.out = out; d.ldo = ldo;
+    return launch_tapgemm(d, st);
+}
+
+int star_conv_t3(const void* X, const void* W3, const void* bias, const void* residual, long long ldres, void* out,
+                 long long ldo, int B, int T, long long HW, int Cin, int Cout, void* stream) {
+    STAR_CHECK_INIT();
+    if (Cin % 8) return fail("star_conv_t3: Cin must be a multiple of 8");
+    if (HW > 0x7fffffffll) return fail("star_conv_t3: HW too large");
+    TapDesc d;
+    memset(&d, 0, sizeof(d));
+    d.A = X;
+    d.adim[0] = Cin; d.adim[1] = HW; d.adim[2] = T; d.adim[3] = B; d.adim[4] = 1;
+    d.astr[1] = Cin; d.astr[2] = (unsigned long long)Cin * HW; d.astr[3] = (unsigned long long)Cin * HW * T;
+    d.astr[4] = (unsigned long long)Cin * HW * T * B;
+    d.on[0] = (int)HW; d.on[1] = T; d.on[2] = B; d.on[3] = 1;
+    d.box[0] = (int)std::min<long long>(TG_BM, HW); d.box[1] = 1; d.box[2] = 1; d.box[3] = 1;
+    if (HW < TG_BM) d.box[1] = (int)std::min<long long>(T, TG_BM / HW);     // small latents: several frames per tile
+    d.ntaps = 3;
+    for (int k = 0; k < 3; ++k) d.tap[k][1] = k - 1;
+    d.K = Cin; d.N = Cout;
+    d.W = W3; d.bias = bias; d.residual = residual; d.ldres = ldres;
+    d.out = out; d.ldo = ldo;
+    return launch_tapgemm(d, (cudaStream_t)stream);
+}
+
+int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, int BT,
+                       int H, int W, int Cout, void* stream) {
+    if (Cout % 8 || Cout / 8 > 64) return fail("star_conv2d_3x3_c4: Cout must be a multiple of 8, <= 512");
+    const int gx = Cout / 8;
+    dim3 block(gx, std::max(1, 256 / gx));
+    const long long npix = (long long)BT * H * W;
+    const long long blocks = (npix + block.y - 1) / block.y;
+    conv3x3_c4_kernel<<<(unsigned)blocks, block, 36 * Cout * sizeof(__half), (cudaStream_t)stream>>>(
+        (const __half*)X, (const __half*)W9, (const __half*)bias, (const __half*)residual, (__half*)out, BT, H, W, Cout);
+    STAR_LAUNCH_CHECK("conv3x3_c4");
+    return 0;
+}
+
+int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                   long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, void* stream) {
+    STAR_CHECK_INIT();
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return fail("star_attention: leading dims must be multiples of 8");
+    if (Nq <= 0 || Nk <= 0 || batch <= 0) return fail("star_attention: empty problem");
+    if (kv_batch_div < 1) kv_batch_div = 1;
+    const int kv_batches = (batch + kv_batch_div - 1) / kv_batch_div;
+    CUtensorMap tq, tk, tv;
+    unsigned box[3] = {AT_D, AT_BQ, 1};
+    {
+        unsigned long long dims[3] = {(unsigned long long)heads * AT_D, (unsigned long long)Nq, (unsigned long long)batch};
+        unsigned long long str[3] = {1, (unsigned long long)ldq, (unsigned long long)ldq * Nq};
+        if (make_tmap(&tq, Q, 3, dims, str, box)) return 1;
+    }
+    {
+        unsigned long long dims[3] = {(unsigned long long)heads * AT_D, (unsigned long long)Nk, (unsigned long long)kv_batches};
+        unsigned long long strk[3] = {1, (unsigned long long)ldk, (unsigned long long)ldk * Nk};
+        unsigned long long strv[3] = {1, (unsigned long long)ldv, (unsigned long long)ldv * Nk};
+        if (make_tmap(&tk, K, 3, dims, strk, box)) return 1;
+        if (make_tmap(&tv, V, 3, dims, strv, box)) return 1;
+    }
+    AttnParams p;
+    p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out = (__half*)O; p.ldo = ldo;
+    dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, batch);
+    if (grid.y > 65535 || grid.z > 65535) return fail("star_attention: grid too large");
+    attn_fwd_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    STAR_LAUNCH_CHECK("attn_fwd");
+    return 0;
+}
+
+int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,
+                            int heads, int Ci, float scale, void* stream) {
+    if (T > TA_MAXT) return fail("star_temporal_attention: T=%d exceeds %d", T, TA_MAXT);
+    if (ld % 8 || ldo % 8 || Ci % 8) return fail("star_temporal_attention: ld/ldo/Ci must be multiples of 8");
+    const long long items = (long long)B * HW * heads;
+    const long long blocks = (items + TA_WARPS - 1) / TA_WARPS;
+    temporal_attn_kernel<<<(unsigned)blocks, TA_WARPS * 32, TA_WARPS * 2 * T * 128, (cudaStream_t)stream>>>(
+        (const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale);
+    STAR_LAUNCH_CHECK("temporal_attn");
+    return 0;
+}
+
+long long star_groupnorm_workspace_bytes(int nsamples, int C) {
+    return (long long)nsamples * 32 * 2 * 8 + (long long)nsamples * C * 2 * 4;
+}
+
+int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out, int nsamples,
+                   long long rows_per_sample, int C, float eps, int silu, void* workspace, void* stream) {
+    if (C % 256 && C % 32) return fail("star_groupnorm: C must be a multiple of 32");
+    if (C % 8) return fail("star_groupnorm: C must be a multiple of 8");
+    if (C / 8 > GN_THREADS) return fail("star_groupnorm: C too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* stats = (double*)workspace;
+    float* ab = (float*)((char*)workspace + (size_t)nsamples * 32 * 2 * 8);
+    STAR_CUDA(cudaMemsetAsync(stats, 0, (size_t)nsamples * 32 * 2 * 8, st));
+    const int lanes = std::max(1, GN_THREADS / (C / 8));
+    const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+    dim3 grid((unsigned)((rows_per_sample + GN_SLAB - 1) / GN_SLAB), nsamples);
+    gn_stats_kernel<<<grid, GN_THREADS, smem, st>>>((const __half*)X, stats, rows_per_sample, C);
+    STAR_LAUNCH_CHECK("gn_stats");
+    gn_finalize_kernel<<<nsamples, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows_per_sample, C, eps);
+    STAR_LAUNCH_CHECK("gn_finalize");
+    const long long total_rows = rows_per_sample * nsamples;
+    gn_apply_kernel<<<grid_for(total_rows * (C / 8), 256), 256, 0, st>>>((const __half*)X, ab, (__half*)out, rows_per_sample,
+                                                                          total_rows, C, silu);
+    STAR_LAUNCH_CHECK("gn_apply");
+    return 0;
+}
+
+int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,
+                   int gate_mode, const void* gate, float w0, float w1, void* stream) {
+    if (C % 8 || C / 8 > 32 * LN_MAX_OCT) return fail("star_layernorm: unsupported C=%d", C);
+    const int wpb = 8;
+    layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const __half*)X, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, C, eps, gate_mode,
+        (const __half*)gate, w0, w1);
+    STAR_LAUNCH_CHECK("layernorm");
+    return 0;
+}
+
+int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* gate, int BT, int H, int W, int C,
+                           void* stream) {
+    if (C % 8) return fail("star_liem_spatial_gate: C must be a multiple of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)BT * H * W;
+    liem_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)X, (__half*)mm_ws, rows, C);
+    STAR_LAUNCH_CHECK("liem_reduce");
+    liem_conv7_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __half*)mm_ws, (const __half*)w98, (__half*)gate,
+                                                                       BT, H, W);
+    STAR_LAUNCH_CHECK("liem_conv7");
+    return 0;
+}
+
+int star_concat_add(const void* a, int Ca, const void* b, const void* c, int Cb, void* out, long long rows,
+                    void* stream) {
+    if (Ca % 8 || Cb % 8) return fail("star_concat_add: channel counts must be multiples of 8");
+    const long long n = rows * ((Ca + Cb) / 8);
+    concat_add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, Ca, (const __half*)b,
+                                                                           (const __half*)c, Cb, (__half*)out, rows);
+    STAR_LAUNCH_CHECK("concat_add");
+    return 0;
+}
+
+int star_add(const void* a, const void* b, void* out, long long n, void* stream) {
+    if (n % 8) return fail("star_add: n must be a multiple of 8");
+    add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (__half*)out, n / 8);
+    STAR_LAUNCH_CHECK("add");
+    return 0;
+}
+
+int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, void* stream) {
+    if (C % 8) return fail("star_upsample2x_crop: C must be a multiple of 8");
+    const long long n = (long long)BT * (2 * H - 2) * (2 * W) * (C / 8);
+    upsample2x_crop_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, BT, H, W, C);
+    STAR_LAUNCH_CHECK("upsample2x_crop");
+    return 0;
+}
+
+int star_nchw5_to_tokens(const void* x_f32, void* out, int B, int C, int F, long long HW, void* stream) {
+    const long long n = (long long)B * F * HW;
+    nchw5_to_tokens_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x_f32, (__half*)out, B, C, F, HW);
+    STAR_LAUNCH_CHECK("nchw5_to_tokens");
+    return 0;
+}
+
+int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, int F, long long HW, void* stream) {
+    const long long n = (long long)B * F * HW;
+    tokens_to_nchw5_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)out, B, C, F, HW);
+    STAR_LAUNCH_CHECK("tokens_to_nchw5");
+    return 0;
+}
+
+int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream) {
+    const int n = B * (dim / 2);
+    sinusoidal_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)t_i64, (__half*)out, B, dim);
+    STAR_LAUNCH_CHECK("sinusoidal");
+    return 0;
+}
+
+int star_silu(const void* x, void* out, long long n, void* stream) {
+    silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, n);
+    STAR_LAUNCH_CHECK("silu");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+"""ctypes binding of libstar_sm100.so (C ABI: include/star_sm100.h).
+
+The library is the only compute backend of star_b200: there is no CPU or
+PyTorch fallback.  ``get_lib()`` raises if the shared object is missing and
+``ensure_init()`` raises if no sm_100 device is available.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstar_sm100.so")
+
+_p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/star_sm100.h one to one
+SIGNATURES = {
+    "star_version": (_i, []),
+    "star_last_error": (ctypes.c_char_p, []),
+    "star_init": (_i, [_i]),
+    "star_linear": (_i, [_p, _ll, _p, _p, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "star_conv2d_3x3": (_i, [_p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p]),
+    "star_conv2d_s2_workspace_bytes": (_ll, [_i, _i, _i, _i]),
+    "star_conv2d_3x3_s2": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _p]),
+    "star_conv_t3": (_i, [_p, _p, _p, _p, _ll, _p, _ll, _i, _i, _ll, _i, _i, _p]),
+    "star_conv2d_3x3_c4": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "star_attention": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _f, _p]),
+    "star_temporal_attention": (_i, [_p, _ll, _p, _ll, _i, _i, _ll, _i, _i, _f, _p]),
+    "star_groupnorm_workspace_bytes": (_ll, [_i, _i]),
+    "star_groupnorm": (_i, [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p]),
+    "star_layernorm": (_i, [_p, _p, _p, _p, _ll, _i, _f, _i, _p, _f, _f, _p]),
+    "star_liem_spatial_gate": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "star_concat_add": (_i, [_p, _i, _p, _p, _i, _p, _ll, _p]),
+    "star_add": (_i, [_p, _p, _p, _ll, _p]),
+    "star_upsample2x_crop": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "star_nchw5_to_tokens": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
+    "star_tokens_to_nchw5": (_i, [_p, _ll, _p, _i, _i, _i, _ll, _p]),
+    "star_sinusoidal": (_i, [_p, _p, _i, _i, _p]),
+    "star_silu": (_i, [_p, _p, _ll, _p]),
+}
+
+_lib = None
+_inited = set()
+
+
+class StarError(RuntimeError):
+    pass
+
+
+def get_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise StarError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). star_b200 has no fallback compute path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return get_lib().star_last_error().decode(errors="replace")
+
+
+def ensure_init(device_index):
+    if device_index in _inited:
+        return
+    rc = get_lib().star_init(int(device_index))
+    if rc != 0:
+        raise StarError("star_init failed: " + last_error())
+    _inited.add(device_index)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise StarError(f"{what}: {last_error()}")

@@ -1,0 +1,247 @@
+"""Tensor-level wrappers over the C ABI (include/star_sm100.h).
+
+PyTorch is used for device memory (torch.empty) and the current CUDA stream
+only; every op below is one call into libstar_sm100.so.  All activations are
+fp16 CUDA tensors in the channels-last token layout X[rows, C] with rows
+ordered (b, t, h, w).
+"""
+import torch
+
+from . import lib as _L
+
+HALF = torch.float16
+
+FLAG_GEGLU = 1
+FLAG_SILU_OUT = 2
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise _L.StarError("star_b200 ops need CUDA tensors (no CPU fallback)")
+    _L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return t.device
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _h(t, name):
+    if t is not None and t.dtype != HALF:
+        raise _L.StarError(f"{name} must be fp16, got {t.dtype}")
+    return t
+
+
+def _rowmajor(t, name):
+    """2-D view whose last dim is contiguous; returns leading dim."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _L.StarError(f"{name} must be a 2-D tensor with contiguous columns")
+    return t.stride(0)
+
+
+def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, out=None):
+    """out[r, n] = epi(sum_k a[r, k] w[n, k]); a may be a strided 2-D view."""
+    _dev(a)
+    _h(a, "a"); _h(w, "w"); _h(bias, "bias"); _h(residual, "residual"); _h(rowvec, "rowvec")
+    lda = _rowmajor(a, "a")
+    rows, K = a.shape
+    n_w = w.shape[0]
+    N = n_w // 2 if (flags & FLAG_GEGLU) else n_w
+    assert w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        out = torch.empty((rows, N), dtype=HALF, device=a.device)
+    ldo = _rowmajor(out, "out")
+    ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    if rowvec is not None:
+        assert rowvec.is_contiguous() and rowvec.shape[-1] == N
+    L = _L.get_lib()
+    _L.check(L.star_linear(_p(a), lda, _p(w), _p(bias), _p(rowvec), int(rowvec_div), _p(residual), ldres,
+                           _p(out), ldo, rows, K, N, flags, _st()), "star_linear")
+    return out
+
+
+def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=None):
+    """x [BT, H, W, Cin] contiguous; w9 [Cout, 3, 3, Cin]; returns [BT*H*W, Cout]."""
+    _dev(x)
+    BT, H, W, Cin = x.shape
+    Cout = w9.shape[0]
+    assert x.is_contiguous() and w9.is_contiguous() and w9.shape[1:] == (3, 3, Cin)
+    if out is None:
+        out = torch.empty((BT * H * W, Cout), dtype=HALF, device=x.device)
+    ldo = _rowmajor(out, "out")
+    ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    L = _L.get_lib()
+    _L.check(L.star_conv2d_3x3(_p(x), _p(w9), _p(bias), _p(rowvec), int(rowvec_div), _p(residual), ldres,
+                               _p(out), ldo, BT, H, W, Cin, Cout, _st()), "star_conv2d_3x3")
+    return out
+
+
+def conv2d_3x3_s2(x, w9, bias=None):
+    """Downsample conv: stride 2, padding (2, 1).  x [BT,H,W,Cin] -> ([BT*Ho*Wo, Cout], Ho, Wo)."""
+    _dev(x)
+    BT, H, W, Cin = x.shape
+    Cout = w9.shape[0]
+    assert x.is_contiguous() and w9.is_contiguous()
+    Ho, Wo = (H + 1) // 2 + 1, (W - 1) // 2 + 1
+    L = _L.get_lib()
+    ws = torch.empty(L.star_conv2d_s2_workspace_bytes(BT, H, W, Cin), dtype=torch.uint8, device=x.device)
+    out = torch.empty((BT * Ho * Wo, Cout), dtype=HALF, device=x.device)
+    _L.check(L.star_conv2d_3x3_s2(_p(x), _p(w9), _p(bias), _p(out), Cout, _p(ws), BT, H, W, Cin, Cout, _st()),
+             "star_conv2d_3x3_s2")
+    return out, Ho, Wo
+
+
+def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
+    """Temporal conv (3,1,1): x [B*T*HW, Cin]; w3 [Cout, 3, Cin]."""
+    _dev(x)
+    rows, Cin = x.shape
+    assert rows == B * T * HW and x.is_contiguous() and w3.is_contiguous()
+    Cout = w3.shape[0]
+    if out is None:
+        out = torch.empty((rows, Cout), dtype=HALF, device=x.device)
+    ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    L = _L.get_lib()
+    _L.check(L.star_conv_t3(_p(x), _p(w3), _p(bias), _p(residual), ldres, _p(out), _rowmajor(out, "out"),
+                            B, T, HW, Cin, Cout, _st()), "star_conv_t3")
+    return out
+
+
+def conv2d_3x3_c4(x, w9, bias=None, residual=None):
+    """Stem conv, x [BT, H, W, 4]; w9 [Cout, 3, 3, 4]."""
+    _dev(x)
+    BT, H, W, C = x.shape
+    assert C == 4 and x.is_contiguous() and w9.is_contiguous()
+    Cout = w9.shape[0]
+    out = torch.empty((BT * H * W, Cout), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_conv2d_3x3_c4(_p(x), _p(w9), _p(bias), _p(residual), _p(out), BT, H, W, Cout, _st()),
+             "star_conv2d_3x3_c4")
+    return out
+
+
+def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=None):
+    """q [batch*Nq, >=heads*64] / k, v [kv_batches*Nk, ...] strided 2-D views (head h at columns h*64..)."""
+    _dev(q)
+    ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
+    if out is None:
+        out = torch.empty((batch * Nq, heads * 64), dtype=HALF, device=q.device)
+    L = _L.get_lib()
+    _L.check(L.star_attention(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), _rowmajor(out, "out"), batch, heads,
+                              Nq, Nk, kv_batch_div, float(scale), _st()), "star_attention")
+    return out
+
+
+def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
+    _dev(qkv)
+    ld = _rowmajor(qkv, "qkv")
+    out = torch.empty((qkv.shape[0], Ci), dtype=HALF, device=qkv.device)
+    L = _L.get_lib()
+    _L.check(L.star_temporal_attention(_p(qkv), ld, _p(out), Ci, B, T, HW, heads, Ci, float(scale), _st()),
+             "star_temporal_attention")
+    return out
+
+
+def groupnorm(x, gamma, beta, nsamples, eps, silu):
+    """x [rows, C]; nsamples equal blocks of rows share statistics."""
+    _dev(x)
+    rows, C = x.shape
+    assert x.is_contiguous() and rows % nsamples == 0
+    L = _L.get_lib()
+    ws = torch.empty(L.star_groupnorm_workspace_bytes(nsamples, C), dtype=torch.uint8, device=x.device)
+    out = torch.empty_like(x)
+    _L.check(L.star_groupnorm(_p(x), _p(gamma), _p(beta), _p(out), nsamples, rows // nsamples, C, float(eps),
+                              int(bool(silu)), _p(ws), _st()), "star_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
+    _dev(x)
+    rows, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    L = _L.get_lib()
+    _L.check(L.star_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), gate_mode, _p(gate),
+                              float(w0), float(w1), _st()), "star_layernorm")
+    return out
+
+
+def liem_spatial_gate(x, w98, BT, H, W):
+    _dev(x)
+    rows, C = x.shape
+    assert rows == BT * H * W and x.is_contiguous()
+    mm = torch.empty((rows, 2), dtype=HALF, device=x.device)
+    gate = torch.empty((rows,), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_liem_spatial_gate(_p(x), _p(w98), _p(mm), _p(gate), BT, H, W, C, _st()),
+             "star_liem_spatial_gate")
+    return gate
+
+
+def concat_add(a, b, c=None):
+    _dev(a)
+    rows, Ca = a.shape
+    Cb = b.shape[1]
+    assert a.is_contiguous() and b.is_contiguous() and (c is None or c.is_contiguous())
+    out = torch.empty((rows, Ca + Cb), dtype=HALF, device=a.device)
+    L = _L.get_lib()
+    _L.check(L.star_concat_add(_p(a), Ca, _p(b), _p(c), Cb, _p(out), rows, _st()), "star_concat_add")
+    return out
+
+
+def add(a, b):
+    _dev(a)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a)
+    L = _L.get_lib()
+    _L.check(L.star_add(_p(a), _p(b), _p(out), a.numel(), _st()), "star_add")
+    return out
+
+
+def upsample2x_crop(x, BT, H, W):
+    _dev(x)
+    C = x.shape[1]
+    out = torch.empty((BT * (2 * H - 2) * (2 * W), C), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_upsample2x_crop(_p(x), _p(out), BT, H, W, C, _st()), "star_upsample2x_crop")
+    return out
+
+
+def nchw5_to_tokens(x):
+    """(b, c, f, h, w) fp32 -> [(b f h w), c] fp16"""
+    _dev(x)
+    x = x.contiguous().float()
+    B, C, F, H, W = x.shape
+    out = torch.empty((B * F * H * W, C), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_nchw5_to_tokens(_p(x), _p(out), B, C, F, H * W, _st()), "star_nchw5_to_tokens")
+    return out
+
+
+def tokens_to_nchw5(x, B, C, F, H, W):
+    _dev(x)
+    out = torch.empty((B, C, F, H, W), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_tokens_to_nchw5(_p(x), _rowmajor(x, "x"), _p(out), B, C, F, H * W, _st()), "star_tokens_to_nchw5")
+    return out
+
+
+def sinusoidal(t, dim):
+    _dev(t)
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=HALF, device=t.device)
+    L = _L.get_lib()
+    _L.check(L.star_sinusoidal(_p(t), _p(out), t.shape[0], dim, _st()), "star_sinusoidal")
+    return out
+
+
+def silu(x):
+    _dev(x)
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    L = _L.get_lib()
+    _L.check(L.star_silu(_p(x), _p(out), x.numel(), _st()), "star_silu")
+    return out

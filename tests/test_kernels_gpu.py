@@ -1,0 +1,217 @@
+"""GPU parity tests: every C-ABI entry point (include/star_sm100.h) against its
+torch reference in oracle/kernel_ref.py on seeded inputs.  Tolerance: fp16
+outputs, fp32 accumulation -> rel-L2 <= 2e-3, max-abs <= 2e-2 * max|ref|
+(the north-star's 1e-3 relative fp16 bound is checked end to end on the UNet
+output in test_unet_gpu.py; single kernels are held to the fp16 rounding of
+their own output)."""
+import pytest
+import torch
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from oracle import kernel_ref as R
+    from star_b200 import ops as O
+    return O, R
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+@pytest.mark.parametrize("rows,K,N,flags,extras", [
+    (128, 64, 128, 0, ""),
+    (300, 320, 320, 0, "bias"),
+    (4096, 1280, 1280, 0, "bias,res"),
+    (1000, 320, 960, 0, ""),
+    (777, 1024, 640, 0, "bias"),
+    (513, 320, 4, 0, "bias"),
+    (1, 320, 1280, 2, "bias"),
+    (2000, 320, 1280, 1, "bias"),
+    (640, 512, 2048, 1, "bias"),
+    (900, 640, 640, 0, "bias,res,rowvec"),
+    (1500, 2560, 320, 0, "bias"),
+])
+def test_linear(env, rows, K, N, flags, extras):
+    O, R = env
+    a = rnd(rows, K, seed=1)
+    w = rnd(N * (2 if flags & 1 else 1), K, seed=2, scale=K ** -0.5)
+    bias = rnd(w.shape[0], seed=3, scale=0.1) if "bias" in extras else None
+    res = rnd(rows, N, seed=4) if "res" in extras else None
+    rowvec = rnd((rows + 299) // 300, N, seed=5) if "rowvec" in extras else None
+    got = O.linear(a, w, bias, res, rowvec, 300, flags)
+    torch.cuda.synchronize()
+    ref = R.linear(a, w, bias, res, rowvec, 300, flags)
+    assert_close(got, ref, what=f"linear {rows}x{K}x{N} flags={flags} {extras}")
+
+
+def test_linear_strided_views(env):
+    O, R = env
+    big = rnd(700, 960, seed=7)
+    a = big[:, 320:640]                       # lda = 960
+    w = rnd(320, 320, seed=8, scale=320 ** -0.5)
+    outbuf = torch.zeros(700, 640, dtype=torch.half, device="cuda")
+    O.linear(a, w, out=outbuf[:, 320:])
+    torch.cuda.synchronize()
+    assert_close(outbuf[:, 320:], R.linear(a, w), what="strided linear")
+    assert (outbuf[:, :320] == 0).all()
+
+
+@pytest.mark.parametrize("BT,H,W,Cin,Cout,extras", [
+    (1, 8, 16, 64, 128, ""),
+    (3, 18, 16, 320, 320, "bias"),
+    (2, 10, 8, 640, 1280, "bias,rowvec"),
+    (2, 17, 27, 320, 4, "bias"),
+    (4, 3, 2, 1280, 1280, "bias,res"),
+    (2, 34, 32, 960, 320, "bias,rowvec,res"),
+])
+def test_conv2d_3x3(env, BT, H, W, Cin, Cout, extras):
+    O, R = env
+    x = rnd(BT, H, W, Cin, seed=1)
+    w9 = rnd(Cout, 3, 3, Cin, seed=2, scale=(9 * Cin) ** -0.5)
+    bias = rnd(Cout, seed=3, scale=0.1) if "bias" in extras else None
+    rowvec = rnd(BT, Cout, seed=4) if "rowvec" in extras else None
+    res = rnd(BT * H * W, Cout, seed=5) if "res" in extras else None
+    got = O.conv2d_3x3(x, w9, bias, rowvec, H * W, res)
+    torch.cuda.synchronize()
+    ref = R.conv2d_3x3(x, w9, bias, rowvec, H * W, res)
+    assert_close(got, ref, what=f"conv3x3 {BT}x{H}x{W} {Cin}->{Cout} {extras}")
+
+
+@pytest.mark.parametrize("BT,H,W,C", [(2, 18, 16, 320), (3, 10, 8, 640), (1, 34, 32, 64), (2, 122, 216, 64)])
+def test_conv2d_s2(env, BT, H, W, C):
+    O, R = env
+    x = rnd(BT, H, W, C, seed=1)
+    w9 = rnd(C, 3, 3, C, seed=2, scale=(9 * C) ** -0.5)
+    bias = rnd(C, seed=3, scale=0.1)
+    got, Ho, Wo = O.conv2d_3x3_s2(x, w9, bias)
+    torch.cuda.synchronize()
+    ref, Hr, Wr = R.conv2d_3x3_s2(x, w9, bias)
+    assert (Ho, Wo) == (Hr, Wr)
+    assert_close(got, ref, what=f"conv s2 {BT}x{H}x{W}x{C}")
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(1, 8, 288, 320), (2, 5, 6, 640), (1, 40, 130, 64), (1, 3, 459, 1280)])
+def test_conv_t3(env, B, T, HW, C):
+    O, R = env
+    x = rnd(B * T * HW, C, seed=1)
+    w3 = rnd(C, 3, C, seed=2, scale=(3 * C) ** -0.5)
+    bias = rnd(C, seed=3, scale=0.1)
+    res = rnd(B * T * HW, C, seed=4)
+    got = O.conv_t3(x, w3, bias, res, B, T, HW)
+    torch.cuda.synchronize()
+    assert_close(got, R.conv_t3(x, w3, bias, res, B, T, HW), what=f"conv_t3 {B},{T},{HW},{C}")
+
+
+def test_conv_c4(env):
+    O, R = env
+    x = rnd(3, 18, 16, 4, seed=1)
+    w9 = rnd(320, 3, 3, 4, seed=2, scale=1 / 6)
+    bias = rnd(320, seed=3, scale=0.1)
+    res = rnd(3 * 18 * 16, 320, seed=4)
+    got = O.conv2d_3x3_c4(x, w9, bias, res)
+    torch.cuda.synchronize()
+    assert_close(got, R.conv2d_3x3_c4(x, w9, bias, res), what="conv c4")
+
+
+@pytest.mark.parametrize("batch,heads,Nq,Nk,div", [
+    (1, 1, 128, 128, 1),
+    (2, 5, 288, 288, 1),
+    (1, 2, 1000, 1000, 1),
+    (8, 5, 288, 77, 4),
+    (1, 2, 4096, 4096, 1),
+    (2, 10, 72, 72, 1),
+])
+def test_attention(env, batch, heads, Nq, Nk, div):
+    O, R = env
+    C = heads * 64
+    kvb = (batch + div - 1) // div
+    if Nq == Nk and div == 1:                      # fused qkv buffer, like the spatial self-attention
+        qkv = rnd(batch * Nq, 3 * C, seed=1)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q = rnd(batch * Nq, C, seed=1)
+        kv = rnd(kvb * Nk, 2 * C, seed=2)
+        k, v = kv[:, :C], kv[:, C:]
+    got = O.attention(q, k, v, batch, heads, Nq, Nk, div, 0.125)
+    torch.cuda.synchronize()
+    ref = R.attention(q, k, v, batch, heads, Nq, Nk, div, 0.125)
+    assert_close(got, ref, what=f"attention b{batch} h{heads} {Nq}x{Nk}")
+
+
+def test_attention_peaky(env):
+    """large logits: exercises the running-max rescale path"""
+    O, R = env
+    q = rnd(1 * 640, 128, seed=1, scale=3.0)
+    k = rnd(1 * 640, 128, seed=2, scale=3.0)
+    v = rnd(1 * 640, 128, seed=3)
+    got = O.attention(q, k, v, 1, 2, 640, 640, 1, 0.125)
+    torch.cuda.synchronize()
+    assert_close(got, R.attention(q, k, v, 1, 2, 640, 640, 1, 0.125), rel=4e-3, what="attention peaky")
+
+
+@pytest.mark.parametrize("B,T,HW,heads,Ci", [(1, 8, 288, 5, 320), (1, 40, 50, 8, 512), (2, 32, 33, 10, 640), (1, 3, 7, 1, 64)])
+def test_temporal_attention(env, B, T, HW, heads, Ci):
+    O, R = env
+    qkv = rnd(B * T * HW, 3 * Ci, seed=1)
+    got = O.temporal_attention(qkv, B, T, HW, heads, Ci)
+    torch.cuda.synchronize()
+    assert_close(got, R.temporal_attention(qkv, B, T, HW, heads, Ci), what="temporal attention")
+
+
+@pytest.mark.parametrize("ns,rps,C,silu", [(8, 288, 320, 1), (1, 8 * 288, 320, 1), (3, 100, 2560, 0), (2, 459, 1280, 1),
+                                           (4, 77, 960, 1), (1, 26352, 640, 0)])
+def test_groupnorm(env, ns, rps, C, silu):
+    O, R = env
+    x = rnd(ns * rps, C, seed=1) + 0.5
+    gamma = (1 + 0.1 * torch.randn(C, device="cuda")).half()
+    beta = (0.1 * torch.randn(C, device="cuda")).half()
+    eps = 1e-5
+    got = O.groupnorm(x, gamma, beta, ns, eps, silu)
+    torch.cuda.synchronize()
+    assert_close(got, R.groupnorm(x, gamma, beta, ns, eps, silu), what=f"groupnorm {ns},{rps},{C}")
+
+
+@pytest.mark.parametrize("rows,C,mode", [(1000, 320, 0), (999, 512, 2), (300, 1280, 1), (64, 640, 2), (5, 320, 1)])
+def test_layernorm(env, rows, C, mode):
+    O, R = env
+    x = rnd(rows, C, seed=1)
+    gamma = (1 + 0.1 * torch.randn(C, device="cuda")).half()
+    beta = (0.1 * torch.randn(C, device="cuda")).half()
+    gate = torch.rand(rows, device="cuda").half() if mode == 1 else None
+    got = O.layernorm(x, gamma, beta, mode, gate, 0.3, -0.7)
+    torch.cuda.synchronize()
+    assert_close(got, R.layernorm(x, gamma, beta, mode, gate, 0.3, -0.7), what=f"layernorm {rows},{C},mode{mode}")
+
+
+def test_liem_spatial_gate(env):
+    O, R = env
+    BT, H, W, C = 3, 18, 16, 320
+    x = rnd(BT * H * W, C, seed=1)
+    w98 = rnd(98, seed=2, scale=0.2)
+    got = O.liem_spatial_gate(x, w98, BT, H, W)
+    torch.cuda.synchronize()
+    assert_close(got, R.liem_spatial_gate(x, w98, BT, H, W), what="liem gate")
+
+
+def test_copies(env):
+    O, R = env
+    a, b, c = rnd(500, 320, seed=1), rnd(500, 640, seed=2), rnd(500, 640, seed=3)
+    assert_close(O.concat_add(a, b, c), R.concat_add(a, b, c), what="concat_add")
+    assert torch.equal(O.concat_add(a, b), R.concat_add(a, b))
+    assert_close(O.add(b, c), R.add(b, c), what="add")
+    x = rnd(2 * 9 * 4, 64, seed=4)
+    assert torch.equal(O.upsample2x_crop(x, 2, 9, 4), R.upsample2x_crop(x, 2, 9, 4))
+    x5 = torch.randn(2, 4, 3, 10, 8, device="cuda")
+    tok = O.nchw5_to_tokens(x5)
+    assert torch.equal(tok, R.nchw5_to_tokens(x5))
+    back = O.tokens_to_nchw5(tok, 2, 4, 3, 10, 8)
+    assert torch.equal(back, R.tokens_to_nchw5(tok, 2, 4, 3, 10, 8))
+    t = torch.tensor([899, 34], device="cuda")
+    assert_close(O.sinusoidal(t, 320), R.sinusoidal(t, 320), rel=2e-3, what="sinusoidal")
+    assert_close(O.silu(a), R.silu(a), what="silu")
