@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the STAR denoising hot path on B200 (driver contract: one JSON line on rank 0).
+
+Metric (BASELINE.json): upscaled frames/sec, 4x 240p->960p I2VGen-XL, 32-frame chunks, 50 steps.
+  * workload (N=1): BASELINE.json configs[1] -- one 32-frame chunk at latent 122x216 (240p -> 960p
+    after pad_to_fit, 976x1728 px), default ControlledV2VUNet (2.04 B parameters, synthetic non-zero
+    weights), CFG 7.5 (2 UNet+ControlNet forwards per solver step), dpmpp_2m_sde 'normal' schedule.
+  * a "step" = ONE solver step of that schedule = 2 forwards + guidance + solver update.
+  * value = output frames / (50 * mean step time): frames per second of the full 50-step denoise
+    (VAE decode is not part of the timed path: the VAE is an un-vendored diffusers module).
+  * N>1: one 32-frame chunk per GPU of a single F=16(N+1)-frame clip (stride 16, as make_chunks
+    produces), exact per-step x0 all-gather (diffusion_sdedit.sample_sr); value counts the unique
+    output frames of the clip.  "scaling": "weak".
+  * e2e: the same metric through VideoToVideo_sr.denoise_latents() from pinned HOST tensors, one
+    1-step call per "step": H2D of latent + text embeddings and D2H of the result inside the timing.
+  * --impl reference: the oracle's CPU/fp32 restatement of the reference path (oracle/unet_ref.py,
+    pinned against the real reference) timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAT_H, LAT_W, CHUNK = 122, 216, 32
+SCHEDULE_STEPS = 50
+METRIC = "upscaled frames/sec, 4x 240p->960p I2VGen-XL, 32-frame chunks, 50 steps"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="star", choices=["star", "reference"])
+    ap.add_argument("--lat-h", type=int, default=LAT_H)
+    ap.add_argument("--lat-w", type=int, default=LAT_W)
+    ap.add_argument("--frames", type=int, default=0, help="override clip length (default 32, or 16(N+1) for N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--trace-out", default="", help="write the per-op time table of the timed region to this file")
+    ap.add_argument("--small", action="store_true", help="reduced model (debug only; not a valid bench line)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def build_model(small, device, seed=2, on_cpu_first=False):
+    from star_b200.utils.synth import synth_state_dict
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    kw = dict(dim_mult=[1, 2, 1, 4], num_res_blocks=1) if small else {}
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**kw)
+    manifest = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth_state_dict(manifest, seed=seed, device="cpu" if on_cpu_first else device)
+    net.load_state_dict({k: v.to(device, torch.float16) for k, v in sd.items()}, assign=True)
+    net.eval()
+    return net, (sd if on_cpu_first else None), kw
+
+
+def synth_inputs(F, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    feat = 0.5 * torch.randn(1, 4, F, H, W, generator=g)
+    y = torch.randn(1, 77, 1024, generator=g)
+    ny = torch.randn(1, 77, 1024, generator=g)
+    return feat, y, ny
+
+
+class _StubText:
+    """Text embeddings are inputs of the hot path (north_star); the OpenCLIP tower is out of scope."""
+
+    def __init__(self, emb):
+        self.emb = emb
+
+    def __call__(self, s):
+        return self.emb
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def cpu_forward_time(sd_cpu, kw, frames, H, W, repeats=1, warm=0):
+    """seconds for ONE oracle forward (fp32, all host threads) on `frames` frames at latent HxW."""
+    from oracle.unet_ref import UNetCfg, controlled_unet_forward
+    feat, y, _ = synth_inputs(frames, H, W, seed=1)
+    x = torch.randn(1, 4, frames, H, W)
+    t = torch.tensor([899])
+    for _ in range(warm):
+        controlled_unet_forward(sd_cpu, x, t, y, feat, UNetCfg(**kw))
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        controlled_unet_forward(sd_cpu, x, t, y, feat, UNetCfg(**kw))
+    return (time.perf_counter() - t0) / repeats
+
+
+def run_reference(args):
+    """--impl reference: the reference path on the host CPU (oracle port, pinned to the real reference)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from star_b200.utils.synth import synth_state_dict
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    from oracle.unet_ref import UNetCfg, controlled_unet_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = dict(dim_mult=[1, 2, 1, 4], num_res_blocks=1) if args.small else {}
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**kw)
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=2)
+    fs, H, W = args.cpu_sample_frames, args.lat_h, args.lat_w
+    feat, y, ny = synth_inputs(fs, H, W, seed=1)
+    x = torch.randn(1, 4, fs, H, W)
+    t = torch.tensor([899])
+
+    def step():                      # one solver step on the sample: 2 CFG forwards + guidance
+        a = controlled_unet_forward(sd, x, t, y, feat, UNetCfg(**kw))
+        b = controlled_unet_forward(sd, x, t, ny, feat, UNetCfg(**kw))
+        return b + 7.5 * (a - b)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = fs / (SCHEDULE_STEPS * dt)
+    sample = (f"{fs} frame(s) of the {CHUNK}-frame chunk at latent {H}x{W}, fp32, one solver step = 2 CFG forwards "
+              f"(per-frame cost of the {CHUNK}-frame chunk extrapolated linearly in frames)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"I2VGen-XL light-deg 4x 240p->960p, {CHUNK}-frame chunk, latent {H}x{W}, 50 steps, CFG 7.5",
+                   "model": "ControlledV2VUNet" + (" (reduced)" if args.small else " 2.04B params"),
+                   "parallelism": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (star_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from star_b200 import ops
+    from star_b200.video_to_video.video_to_video_model import VideoToVideo_sr, make_chunks
+
+    H, W = args.lat_h, args.lat_w
+    F = args.frames or (CHUNK if world == 1 else 16 * (world + 1))
+    want_cpu = (world == 1 and rank == 0 and not args.no_cpu_baseline)
+    net, sd_cpu, kw = build_model(args.small, dev, on_cpu_first=want_cpu)
+    feat, y, ny = synth_inputs(F, H, W)
+    feat_pin, y_pin, ny_pin = feat.pin_memory(), y.pin_memory(), ny.pin_memory()
+
+    class Opt:
+        model_path = None
+    pipe = VideoToVideo_sr(Opt(), device=dev, text_encoder=_StubText(ny.to(dev)), vae=object(), generator=net)
+    n_chunks = len(make_chunks(F, 0, CHUNK)) if F > CHUNK else 1
+
+    feat_d, y_d, ny_d = feat.to(dev), y.to(dev), ny.to(dev)
+
+    def run_steps(k):
+        return pipe.denoise_latents(feat_d, y_d, ny_d, total_noise_levels=1000, steps=k, solver_mode="normal",
+                                    guide_scale=7.5, max_chunk_len=CHUNK)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also packs the weights) -------------------------------------------------------
+    import logging
+    logging.getLogger("star_b200").setLevel(logging.ERROR)
+    if args.warmup > 0:
+        run_steps(args.warmup)
+    barrier()
+
+    # ---- timed: exactly K solver steps, device-resident inputs ----------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = ops.launch_count()
+    ops.trace_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    out = run_steps(args.steps)
+    ev1.record()
+    barrier()
+    trace = ops.trace_end()
+    launches = ops.launch_count() - n0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    ms_per_step = ms / args.steps
+    value = F / (SCHEDULE_STEPS * ms_per_step / 1e3)
+
+    # ---- e2e: host buffers, one 1-step API call per step ----------------------------------------
+    def e2e_step():
+        o = pipe.denoise_latents(feat_pin, y_pin, ny_pin, total_noise_levels=1000, steps=1, solver_mode="normal",
+                                 guide_scale=7.5, max_chunk_len=CHUNK)
+        return o.cpu()
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = tt.item()
+    e2e_value = F / (SCHEDULE_STEPS * (e2e_ms / args.steps) / 1e3)
+    h2d = feat.numel() * 4 + y.numel() * 4 + ny.numel() * 4
+    d2h = res.numel() * res.element_size()
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: spatial self-attention at the finest level ------------
+    hw0 = H * W
+    per_op = {}
+    attn_ms = []
+    for name, sig, t_ms in trace:
+        per_op[name] = per_op.get(name, 0.0) + t_ms
+        if name == "attention" and len(sig) >= 7 and sig[5] == hw0 and sig[6] == hw0:
+            attn_ms.append((sig, t_ms))
+    peaks = measured_peaks()
+    roof = None
+    if attn_ms:
+        sig = attn_ms[0][0]
+        batch, heads = sig[3], sig[4]
+        flops = 4.0 * hw0 * hw0 * 64 * batch * heads
+        avg = sum(t for _, t in attn_ms) / len(attn_ms)
+        ach = flops / (avg * 1e-3) / 1e12
+        roof = {"kernel": "attn_fwd_kernel (spatial self-attention, finest level)", "bound": "tensor",
+                "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                "peak_source": peaks["source"], "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg,
+                "launches_timed": len(attn_ms), "traffic": None,
+                "share_of_step": sum(t for _, t in attn_ms) / sum(per_op.values())}
+    if args.trace_out and rank == 0:
+        tot = sum(per_op.values())
+        with open(args.trace_out, "w") as f:
+            f.write(f"# per-op device time inside the timed region ({args.steps} solver steps, CUDA events)\n")
+            for k, v in sorted(per_op.items(), key=lambda kv: -kv[1]):
+                f.write(f"{k:24s} {v:12.3f} ms  {100 * v / tot:6.2f} %\n")
+            f.write(f"total traced {tot:.3f} ms; wall (events) {ms:.3f} ms\n")
+
+    # ---- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample ---------------
+    cpu = None
+    if want_cpu:
+        del pipe, net
+        torch.cuda.empty_cache()
+        torch.set_num_threads(os.cpu_count() or 1)
+        fs = args.cpu_sample_frames
+        t_fwd = cpu_forward_time(sd_cpu, kw, fs, H, W)
+        cpu_val = fs / (SCHEDULE_STEPS * 2 * t_fwd)
+        cpu = {"value": cpu_val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 oracle forward (fp32) on {fs} frame(s) at latent {H}x{W}: {t_fwd:.1f} s; "
+                         f"x2 CFG forwards x50 steps, linear in frames"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"I2VGen-XL light-deg 4x 240p->960p, {F}-frame clip as {n_chunks} chunk(s) of {CHUNK}, "
+                                   f"latent {H}x{W}, 50-step dpmpp_2m_sde, CFG 7.5 (2 forwards/step)",
+                       "model": "ControlledV2VUNet" + (" (reduced, debug)" if args.small else " 2.04B params, synthetic weights"),
+                       "frames": F, "chunks": n_chunks, "global_batch": 1,
+                       "parallelism": f"chunk-parallel x{world}, per-step x0 all-gather" if world > 1 else "single GPU",
+                       "l2": "activations (0.54 GB per tensor) exceed the 126 MB L2; no explicit flush",
+                       "step": "one solver step = 2 UNet+ControlNet forwards + guidance + solver update",
+                       "vae": "not timed (un-vendored diffusers module; latent in / latent out)"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "VideoToVideo_sr.denoise_latents(host tensors, steps=1).cpu() per step"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "op_time_share": {k: round(v / sum(per_op.values()), 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

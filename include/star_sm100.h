@@ -25,6 +25,8 @@ extern "C" {
 
 int star_version(void);
 const char* star_last_error(void);
+/* number of kernels this library has launched since it was loaded (all streams) */
+long long star_launch_count(void);
 /* Resolve cuTensorMapEncodeTiled, opt kernels into >48 KB shared memory.  Fails on non-sm_100 devices. */
 int star_init(int device);
 

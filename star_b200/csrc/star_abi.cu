@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -21,6 +22,7 @@ namespace {
 thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
+std::atomic<long long> g_launches{0};
 
 int fail(const char* fmt, ...) {
     char buf[1024];
@@ -41,6 +43,7 @@ int fail(const char* fmt, ...) {
     } while (0)
 #define STAR_LAUNCH_CHECK(name)                                                             \
     do {                                                                                    \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
         cudaError_t e_ = cudaGetLastError();                                                \
         if (e_ != cudaSuccess) return fail("launch %s failed: %s", name, cudaGetErrorString(e_)); \
     } while (0)
@@ -163,6 +166,7 @@ extern "C" {
 
 int star_version(void) { return 100; }
 const char* star_last_error(void) { return g_err.c_str(); }
+long long star_launch_count(void) { return g_launches.load(); }
 
 int star_init(int device) {
     STAR_CUDA(cudaSetDevice(device));

@@ -16,6 +16,7 @@ _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_flo
 SIGNATURES = {
     "star_version": (_i, []),
     "star_last_error": (ctypes.c_char_p, []),
+    "star_launch_count": (_ll, []),
     "star_init": (_i, [_i]),
     "star_linear": (_i, [_p, _ll, _p, _p, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
     "star_conv2d_3x3": (_i, [_p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p]),

@@ -15,6 +15,47 @@ FLAG_GEGLU = 1
 FLAG_SILU_OUT = 2
 
 
+# ---- optional per-op tracing (CUDA events on the launching stream) ---------------------------------
+_trace = None
+
+
+def trace_begin():
+    """Start recording (name, signature, start_event, end_event) for every op call."""
+    global _trace
+    _trace = []
+
+
+def trace_end():
+    """Stop recording; returns [(name, signature, milliseconds)] (synchronises the device)."""
+    global _trace
+    rec, _trace = _trace, None
+    torch.cuda.synchronize()
+    return [(n, sig, a.elapsed_time(b)) for (n, sig, a, b) in (rec or [])]
+
+
+def _traced(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        if _trace is None:
+            return fn(*args, **kw)
+        sig = tuple(tuple(a.shape) if torch.is_tensor(a) else a for a in args
+                    if torch.is_tensor(a) or isinstance(a, (int, float)))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kw)
+        b.record()
+        _trace.append((fn.__name__, sig, a, b))
+        return out
+    return wrapper
+
+
+def launch_count():
+    """Kernels launched by libstar_sm100.so since load."""
+    return _L.get_lib().star_launch_count()
+
+
 def _dev(t):
     if not t.is_cuda:
         raise _L.StarError("star_b200 ops need CUDA tensors (no CPU fallback)")
@@ -43,6 +84,7 @@ def _rowmajor(t, name):
     return t.stride(0)
 
 
+@_traced
 def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, out=None):
     """out[r, n] = epi(sum_k a[r, k] w[n, k]); a may be a strided 2-D view."""
     _dev(a)
@@ -64,6 +106,7 @@ def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, o
     return out
 
 
+@_traced
 def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=None):
     """x [BT, H, W, Cin] contiguous; w9 [Cout, 3, 3, Cin]; returns [BT*H*W, Cout]."""
     _dev(x)
@@ -80,6 +123,7 @@ def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=N
     return out
 
 
+@_traced
 def conv2d_3x3_s2(x, w9, bias=None):
     """Downsample conv: stride 2, padding (2, 1).  x [BT,H,W,Cin] -> ([BT*Ho*Wo, Cout], Ho, Wo)."""
     _dev(x)
@@ -95,6 +139,7 @@ def conv2d_3x3_s2(x, w9, bias=None):
     return out, Ho, Wo
 
 
+@_traced
 def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
     """Temporal conv (3,1,1): x [B*T*HW, Cin]; w3 [Cout, 3, Cin]."""
     _dev(x)
@@ -110,6 +155,7 @@ def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
     return out
 
 
+@_traced
 def conv2d_3x3_c4(x, w9, bias=None, residual=None):
     """Stem conv, x [BT, H, W, 4]; w9 [Cout, 3, 3, 4]."""
     _dev(x)
@@ -123,6 +169,7 @@ def conv2d_3x3_c4(x, w9, bias=None, residual=None):
     return out
 
 
+@_traced
 def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=None):
     """q [batch*Nq, >=heads*64] / k, v [kv_batches*Nk, ...] strided 2-D views (head h at columns h*64..)."""
     _dev(q)
@@ -135,6 +182,7 @@ def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=No
     return out
 
 
+@_traced
 def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
     _dev(qkv)
     ld = _rowmajor(qkv, "qkv")
@@ -145,6 +193,7 @@ def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
     return out
 
 
+@_traced
 def groupnorm(x, gamma, beta, nsamples, eps, silu):
     """x [rows, C]; nsamples equal blocks of rows share statistics."""
     _dev(x)
@@ -158,6 +207,7 @@ def groupnorm(x, gamma, beta, nsamples, eps, silu):
     return out
 
 
+@_traced
 def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
     _dev(x)
     rows, C = x.shape
@@ -169,6 +219,7 @@ def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
     return out
 
 
+@_traced
 def liem_spatial_gate(x, w98, BT, H, W):
     _dev(x)
     rows, C = x.shape
@@ -181,6 +232,7 @@ def liem_spatial_gate(x, w98, BT, H, W):
     return gate
 
 
+@_traced
 def concat_add(a, b, c=None):
     _dev(a)
     rows, Ca = a.shape
@@ -192,6 +244,7 @@ def concat_add(a, b, c=None):
     return out
 
 
+@_traced
 def add(a, b):
     _dev(a)
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
@@ -201,6 +254,7 @@ def add(a, b):
     return out
 
 
+@_traced
 def upsample2x_crop(x, BT, H, W):
     _dev(x)
     C = x.shape[1]
@@ -210,6 +264,7 @@ def upsample2x_crop(x, BT, H, W):
     return out
 
 
+@_traced
 def nchw5_to_tokens(x):
     """(b, c, f, h, w) fp32 -> [(b f h w), c] fp16"""
     _dev(x)
@@ -221,6 +276,7 @@ def nchw5_to_tokens(x):
     return out
 
 
+@_traced
 def tokens_to_nchw5(x, B, C, F, H, W):
     _dev(x)
     out = torch.empty((B, C, F, H, W), dtype=HALF, device=x.device)
@@ -229,6 +285,7 @@ def tokens_to_nchw5(x, B, C, F, H, W):
     return out
 
 
+@_traced
 def sinusoidal(t, dim):
     _dev(t)
     t = t.to(torch.int64).contiguous()
@@ -238,6 +295,7 @@ def sinusoidal(t, dim):
     return out
 
 
+@_traced
 def silu(x):
     _dev(x)
     assert x.is_contiguous()

@@ -1,0 +1,198 @@
+"""Pipeline entry of STAR video super-resolution on star_b200.
+
+Mirrors ``VideoToVideo_sr`` of the reference's video_to_video/video_to_video_model.py
+(:20-139: constructor, ``test``; :141-161 VAE helpers; :164-210 ``pad_to_fit`` /
+``make_chunks`` / ``sliding_windows_1d``).  What differs:
+
+* the denoiser is star_b200's ``ControlledV2VUNet`` (sm_100a kernels), not autocast PyTorch;
+* the diffusion block of ``test`` (ref :98-123) is factored into ``denoise_latents`` so that
+  the latent-in / latent-out hot path can be driven (and benchmarked) without the VAE;
+* the text encoder (open_clip) and the temporal VAE (diffusers) are un-vendored third-party
+  packages: they are imported lazily, and ready-made objects can be injected
+  (``text_encoder=``, ``vae=``, ``generator=``), which is how the tests and the benchmark run
+  on boxes without those packages or checkpoints;
+* with ``torch.distributed`` initialised, frame chunks are sharded across ranks
+  (diffusion_sdedit.GaussianDiffusion.sample_sr, ``chunk_parallel``).
+"""
+from typing import Any, Dict
+
+import torch
+import torch.nn.functional as F
+
+from .diffusion.diffusion_sdedit import GaussianDiffusion
+from .diffusion.schedules_sdedit import noise_schedule
+from .modules.unet_v2v import ControlledV2VUNet, rearrange
+from .utils.config import cfg
+from .utils.logger import get_logger
+
+logger = get_logger()
+
+__all__ = ["VideoToVideo_sr", "pad_to_fit", "make_chunks", "sliding_windows_1d"]
+
+
+class VideoToVideo_sr():
+    def __init__(self, opt, device=torch.device('cuda:0'), text_encoder=None, vae=None, generator=None):
+        self.opt = opt
+        self.device = device
+
+        if text_encoder is None:
+            from .modules.embedder import FrozenOpenCLIPEmbedder
+            text_encoder = FrozenOpenCLIPEmbedder(device=self.device, pretrained="laion2b_s32b_b79k")
+            text_encoder.model.to(self.device)
+            logger.info('Build encoder with FrozenOpenCLIPEmbedder')
+        self.text_encoder = text_encoder
+
+        if generator is None:
+            generator = ControlledV2VUNet().to(self.device).eval()
+            cfg.model_path = opt.model_path
+            load_dict = torch.load(cfg.model_path, map_location='cpu')
+            if 'state_dict' in load_dict:
+                load_dict = load_dict['state_dict']
+            ret = generator.load_state_dict(load_dict, strict=False)
+            logger.info('Load model path {}, with local status {}'.format(cfg.model_path, ret))
+        self.generator = generator.half()
+
+        sigmas = noise_schedule(schedule='logsnr_cosine_interp', n=1000, zero_terminal_snr=True,
+                                scale_min=2.0, scale_max=4.0)
+        self.diffusion = GaussianDiffusion(sigmas=sigmas)
+
+        if vae is None:
+            try:
+                from diffusers import AutoencoderKLTemporalDecoder
+            except ImportError as e:                                 # pragma: no cover
+                raise ImportError("VideoToVideo_sr needs diffusers' AutoencoderKLTemporalDecoder for pixel I/O; "
+                                  "pass vae=... or use denoise_latents() for the latent-space path") from e
+            vae = AutoencoderKLTemporalDecoder.from_pretrained(
+                "stabilityai/stable-video-diffusion-img2vid", subfolder="vae", variant="fp16")
+            vae.eval()
+            vae.requires_grad_(False)
+            vae.to(self.device)
+        self.vae = vae
+
+        self.negative_prompt = cfg.negative_prompt
+        self.positive_prompt = cfg.positive_prompt
+        self.negative_y = self._encode_text(self.negative_prompt)
+
+    def _encode_text(self, y):
+        """str -> (1,77,1024) via the text encoder; tensors pass through (precomputed embedding)."""
+        if torch.is_tensor(y):
+            return y.to(self.device)
+        return self.text_encoder(y).detach()
+
+    # -- latent-space hot path (ref :98-123) ------------------------------------------------------
+    @torch.no_grad()
+    def denoise_latents(self, video_data_feature, y, negative_y=None, total_noise_levels=1000, steps=50,
+                        solver_mode='fast', guide_scale=7.5, max_chunk_len=32, noise=None, noise_sampler=None,
+                        chunk_parallel="auto"):
+        """video_data_feature: (1,4,F,h,w) VAE latent of the upsampled LR clip (any device; moved to
+        self.device), y / negative_y: (1,77,1024).  Returns the denoised latent (1,4,F,h,w) fp32 on
+        self.device.  ``noise`` / ``noise_sampler`` pin the two random inputs (diffuse noise, SDE noise)."""
+        feat = video_data_feature.to(self.device, torch.float32)
+        y = y.to(self.device)
+        negative_y = (self.negative_y if negative_y is None else negative_y).to(self.device)
+        frames_num = feat.shape[2]
+        t = torch.LongTensor([total_noise_levels - 1]).to(self.device)
+        noised_lr = self.diffusion.diffuse(feat, t, noise=noise)
+        model_kwargs = [{'y': y}, {'y': negative_y}, {'hint': feat}]
+        chunk_inds = make_chunks(frames_num, interp_f_num=0, max_chunk_len=max_chunk_len) \
+            if frames_num > max_chunk_len else None
+        extra = {} if noise_sampler is None else {'noise_sampler': noise_sampler}
+        return self.diffusion.sample_sr(
+            noise=noised_lr, model=self.generator, model_kwargs=model_kwargs, guide_scale=guide_scale,
+            guide_rescale=0.2, solver='dpmpp_2m_sde', solver_mode=solver_mode, return_intermediate=None,
+            steps=steps, t_max=total_noise_levels - 1, t_min=0, discretization='trailing',
+            chunk_inds=chunk_inds, chunk_parallel=chunk_parallel, **extra)
+
+    # -- pixel-space entry (ref :75-139) ------------------------------------------------------------
+    @torch.no_grad()
+    def test(self, input: Dict[str, Any], total_noise_levels=1000, steps=50, solver_mode='fast', guide_scale=7.5,
+             max_chunk_len=32):
+        video_data = input['video_data']
+        y = input['y']
+        (target_h, target_w) = input['target_res']
+        video_data = F.interpolate(video_data, [target_h, target_w], mode='bilinear')
+        logger.info(f'video_data shape: {video_data.shape}')
+        frames_num, _, h, w = video_data.shape
+        padding = pad_to_fit(h, w)
+        video_data = F.pad(video_data, padding, 'constant', 1)
+        video_data = video_data.unsqueeze(0).to(self.device)
+        bs = 1
+        video_data_feature = self.vae_encode(video_data)
+        y = self._encode_text(y)
+        gen_vid = self.denoise_latents(video_data_feature, y, None, total_noise_levels, steps, solver_mode,
+                                       guide_scale, max_chunk_len)
+        logger.info('sampling, finished.')
+        with torch.autocast('cuda', enabled=torch.cuda.is_available()):
+            vid_tensor_gen = self.vae_decode_chunk(gen_vid, chunk_size=3)
+        logger.info('temporal vae decoding, finished.')
+        w1, w2, h1, h2 = padding
+        vid_tensor_gen = vid_tensor_gen[:, :, h1:h + h1, w1:w + w1]
+        gen_video = rearrange(vid_tensor_gen, '(b f) c h w -> b c f h w', b=bs)
+        return gen_video.type(torch.float32).cpu()
+
+    # -- VAE helpers (ref :141-161): exact 3-frame decode windows, 1-frame encode ----------------------
+    def temporal_vae_decode(self, z, num_f):
+        return self.vae.decode(z / self.vae.config.scaling_factor, num_frames=num_f).sample
+
+    def vae_decode_chunk(self, z, chunk_size=3):
+        z = rearrange(z, "b c f h w -> (b f) c h w")
+        video = []
+        for ind in range(0, z.shape[0], chunk_size):
+            num_f = z[ind:ind + chunk_size].shape[0]
+            video.append(self.temporal_vae_decode(z[ind:ind + chunk_size], num_f))
+        return torch.cat(video)
+
+    def vae_encode(self, t, chunk_size=1):
+        num_f = t.shape[1]
+        t = rearrange(t, "b f c h w -> (b f) c h w")
+        z_list = []
+        for ind in range(0, t.shape[0], chunk_size):
+            z_list.append(self.vae.encode(t[ind:ind + chunk_size]).latent_dist.sample())
+        z = rearrange(torch.cat(z_list, dim=0), "(b f) c h w -> b c f h w", f=num_f)
+        return z * self.vae.config.scaling_factor
+
+
+def _centre_pad(size, target):
+    lo = int((target - size) // 2)
+    return lo, target - lo - size
+
+
+def pad_to_fit(h, w):
+    """(w1, w2, h1, h2) for F.pad (ref :164-187): small inputs are centred in 720x1280; larger ones
+    are padded bottom/right so that H = 16 (mod 64) and W = 0 (mod 64) -> latent H = 2 (mod 8)."""
+    best_h, best_w = 720, 1280
+    if h < best_h:
+        h1, h2 = _centre_pad(h, best_h)
+    elif h == best_h:
+        h1 = h2 = 0
+    else:
+        h1, h2 = 0, int((h + 48) // 64 * 64) + 64 - 48 - h
+    if w < best_w:
+        w1, w2 = _centre_pad(w, best_w)
+    elif w == best_w:
+        w1 = w2 = 0
+    else:
+        w1, w2 = 0, int(w // 64 * 64) + 64 - w
+    return (w1, w2, h1, h2)
+
+
+def sliding_windows_1d(length, window_size, overlap_size):
+    """Windows of ``window_size`` with stride window-overlap; the last window absorbs the remainder
+    when fewer than 1.25 windows are left (ref :199-210)."""
+    stride = window_size - overlap_size
+    coords, ind = [], 0
+    while ind < length:
+        if ind + window_size * 1.25 >= length:
+            coords.append((ind, length))
+            break
+        coords.append((ind, ind + window_size))
+        ind += stride
+    return coords
+
+
+def make_chunks(f_num, interp_f_num, max_chunk_len, chunk_overlap_ratio=0.5):
+    """Chunk index list for a clip of f_num frames (ref :190-196)."""
+    max_o_len = max_chunk_len * chunk_overlap_ratio
+    chunk_len = int((max_chunk_len - 1) // (1 + interp_f_num) * (interp_f_num + 1) + 1)
+    o_len = int((max_o_len - 1) // (1 + interp_f_num) * (interp_f_num + 1) + 1)
+    return sliding_windows_1d(f_num, chunk_len, o_len)
