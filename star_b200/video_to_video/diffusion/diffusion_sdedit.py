@@ -163,6 +163,12 @@ class GaussianDiffusion(object):
                 and dist.is_available() and dist.is_initialized():
             world, rank = dist.get_world_size(), dist.get_rank()
         mode = "exact" if chunk_parallel == "auto" else chunk_parallel
+        if world > 1 and solver == 'dpmpp_2m_sde' and kwargs.get('noise_sampler') is None:
+            # every rank applies the same solver update: share the SDE noise stream (rank 0's seed)
+            from .solvers_sdedit import IntervalNoiseSampler
+            sd = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(noise.device)
+            dist.broadcast(sd, 0)
+            kwargs['noise_sampler'] = IntervalNoiseSampler(noise, seed=int(sd.item()))
 
         def eval_x0(xt, sigma, variant_info=None):
             t = self._sigma_to_t(sigma).repeat(len(xt)).round().long()
@@ -285,8 +291,12 @@ class GaussianDiffusion(object):
                 t = self._sigma_to_t(sigma).repeat(len(xt)).round().long()
                 return self.denoise(xt, t, None, model, kw, guide_scale, guide_rescale, clamp, percentile,
                                     variant_info=variant_info)[-2]
+            kw_i = dict(kwargs)
+            if kw_i.get('noise_sampler') is not None:       # injected full-clip noise: use this chunk's frames
+                full = kw_i['noise_sampler']
+                kw_i['noise_sampler'] = lambda a, b, full=full, s=s, e=e: full(a, b)[:, :, s:e]
             xi = solver_fn(noise[:, :, s:e].clone(), fn, sigmas, variant_info=variant_info,
-                           show_progress=show_progress, **kwargs)
+                           show_progress=show_progress, **kw_i)
             lo, hi = keep[i]
             outs.append(xi[:, :, lo:hi])
         send = noise.new_zeros((b, c, pad, h, w))

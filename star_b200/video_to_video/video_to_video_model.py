@@ -93,6 +93,9 @@ class VideoToVideo_sr():
         frames_num = feat.shape[2]
         t = torch.LongTensor([total_noise_levels - 1]).to(self.device)
         noised_lr = self.diffusion.diffuse(feat, t, noise=noise)
+        if noise is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            torch.distributed.broadcast(noised_lr, 0)       # chunk-parallel ranks start from the same sample
         model_kwargs = [{'y': y}, {'y': negative_y}, {'hint': feat}]
         chunk_inds = make_chunks(frames_num, interp_f_num=0, max_chunk_len=max_chunk_len) \
             if frames_num > max_chunk_len else None
