@@ -177,3 +177,38 @@ STAR_DEVINL uint32_t pack_half2(float a, float b) {
 }
 
 }  // namespace star
+
+namespace star {
+// 32 lanes x 32 columns: registers -> TMEM (thread i writes lane i of the warp's quadrant)
+STAR_DEVINL void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+STAR_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+STAR_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max rel. error 7.7e-5, below the fp16 rounding of the probabilities), exponent inserted
+// with one integer add.  Valid for x in [-126, 126].
+STAR_DEVINL float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float magic = 12582912.0f;                 // 1.5 * 2^23
+    const float fr = __fadd_rn(x, magic);            // integer part lands in the low mantissa bits
+    const float f = __fsub_rn(x, __fsub_rn(fr, magic));
+    float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+    p = fmaf(p, f, 0.6932762265205383f);
+    p = fmaf(p, f, 0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(fr) << 23));
+}
+}  // namespace star

@@ -7,11 +7,13 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "../../include/star_sm100.h"
 #include "attn.cuh"
+#include "attn2.cuh"
 #include "rowops.cuh"
 #include "tapgemm.cuh"
 
@@ -22,6 +24,8 @@ namespace {
 thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
+int g_attn_impl = 0;   // 0 auto, 1 = one-tile kernel, 2 = two-tile ping-pong kernel (debug override STAR_ATTN_IMPL)
+int g_attn_poly = 4;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
 std::atomic<long long> g_launches{0};
 
 int fail(const char* fmt, ...) {
@@ -184,6 +188,12 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<128>::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<160>::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    if (const char* e = getenv("STAR_ATTN_IMPL")) g_attn_impl = atoi(e);
+    if (const char* e = getenv("STAR_ATTN_POLY")) g_attn_poly = atoi(e);
     STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TA_WARPS * 2 * TA_MAXT * 128));
     return 0;
@@ -334,8 +344,21 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
+    if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
+    const bool two_tile = g_attn_impl == 2 || (g_attn_impl == 0 && Nk > AT_BKV && Nq > AT_BQ);
+    if (two_tile) {
+        dim3 grid((Nq + 255) / 256, heads, batch);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (g_attn_poly) {
+            case 0: attn2_fwd_kernel<0><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 2: attn2_fwd_kernel<2><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 3: attn2_fwd_kernel<3><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            default: attn2_fwd_kernel<4><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+        }
+        STAR_LAUNCH_CHECK("attn2_fwd");
+        return 0;
+    }
     dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, batch);
-    if (grid.y > 65535 || grid.z > 65535) return fail("star_attention: grid too large");
     attn_fwd_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
     STAR_LAUNCH_CHECK("attn_fwd");
     return 0;
