@@ -25,7 +25,7 @@ thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
 int g_attn_impl = 0;   // 0 auto, 1 = one-tile kernel, 2 = two-tile ping-pong kernel (debug override STAR_ATTN_IMPL)
-int g_attn_poly = 4;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
+int g_attn_poly = 0;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
 std::atomic<long long> g_launches{0};
 
 int fail(const char* fmt, ...) {
