@@ -14,8 +14,10 @@
 #include "../../include/star_sm100.h"
 #include "attn.cuh"
 #include "attn2.cuh"
+#include "attn3.cuh"
 #include "rowops.cuh"
 #include "tapgemm.cuh"
+#include "tapgemm2.cuh"
 
 using namespace star;
 
@@ -24,7 +26,8 @@ namespace {
 thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
-int g_attn_impl = 0;   // 0 auto, 1 = one-tile kernel, 2 = two-tile ping-pong kernel (debug override STAR_ATTN_IMPL)
+int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
+int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
 int g_attn_poly = 0;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
 std::atomic<long long> g_launches{0};
 
@@ -54,7 +57,8 @@ int fail(const char* fmt, ...) {
 
 // rank-`rank` fp16 tensor map, dims[0] innermost (contiguous), strides in ELEMENTS for dims 1..rank-1
 int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
-              const unsigned long long* strides_elems, const unsigned* box) {
+              const unsigned long long* strides_elems, const unsigned* box,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) {
@@ -69,7 +73,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
     }
     if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
@@ -144,8 +148,85 @@ int launch_tapgemm_bn(const TapDesc& d, cudaStream_t st) {
     return 0;
 }
 
+template <int BN>
+int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    long long m_tiles = 1;
+    int box_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.on[i] = d.on[i];
+        p.box[i] = d.box[i];
+        p.tiles[i] = (d.on[i] + d.box[i] - 1) / d.box[i];
+        m_tiles *= p.tiles[i];
+        box_rows *= d.box[i];
+    }
+    if (box_rows > TG_BM) return fail("tapgemm2: box has %d rows (> %d)", box_rows, TG_BM);
+    p.box_rows = box_rows;
+    p.ntaps = d.ntaps;
+    memcpy(p.tap, d.tap, sizeof(p.tap));
+    p.K = d.K;
+    p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
+    p.N = d.N;
+    p.flags = d.flags;
+    p.bias = (const __half*)d.bias;
+    p.rowvec = (const __half*)d.rowvec;
+    p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
+    p.residual = (const __half*)d.residual;
+    p.res_ld = d.ldres;
+    p.out = (__half*)d.out;
+    p.out_ld = d.ldo;
+    const bool geglu = d.flags & TG_GEGLU;
+    const int n_per_tile = geglu ? BN / 2 : BN;
+    TapGemm2Extra ex;
+    ex.n_tiles = (d.N + n_per_tile - 1) / n_per_tile;
+    const long long total = m_tiles * ex.n_tiles;
+    if (total > 0x7fffffffll) return fail("tapgemm2: too many tiles");
+    ex.num_tiles = (int)total;
+
+    CUtensorMap ta, tw, to, tr;
+    unsigned abox[5] = {TG_BK, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
+    if (make_tmap(&ta, d.A, 5, d.adim, d.astr, abox)) return 1;
+    const unsigned long long wrows = geglu ? 2ull * d.N : (unsigned long long)d.N;
+    unsigned long long wdim[2] = {(unsigned long long)d.ntaps * d.K, wrows};
+    unsigned long long wstr[2] = {1, (unsigned long long)d.ntaps * d.K};
+    unsigned wbox[2] = {TG_BK, (unsigned)(geglu ? BN / 2 : BN)};
+    if (make_tmap(&tw, d.W, 2, wdim, wstr, wbox)) return 1;
+    // output / residual: (N, n1..n4) with row pitch ld; 32-column boxes, SWIZZLE_64B staging tiles
+    unsigned obox[5] = {32, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
+    unsigned long long odim[5] = {(unsigned long long)d.N, (unsigned long long)d.on[0], (unsigned long long)d.on[1],
+                                  (unsigned long long)d.on[2], (unsigned long long)d.on[3]};
+    auto strides = [&](long long ld, unsigned long long* s) {
+        s[0] = 1;
+        s[1] = (unsigned long long)ld;
+        s[2] = s[1] * d.on[0];
+        s[3] = s[2] * d.on[1];
+        s[4] = s[3] * d.on[2];
+    };
+    unsigned long long ostr[5], rstr[5];
+    strides(d.ldo, ostr);
+    if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (d.residual) {
+        strides(d.ldres, rstr);
+        if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    } else {
+        tr = to;
+    }
+    const int grid = (int)std::min<long long>(total, g_num_sms);
+    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::TOTAL, st>>>(ta, tw, to, tr, p, ex);
+    STAR_LAUNCH_CHECK("tapgemm2");
+    return 0;
+}
+
 int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     const bool geglu = d.flags & TG_GEGLU;
+    const bool aligned = (d.N % 32 == 0) && (d.ldo % 8 == 0) && (reinterpret_cast<uintptr_t>(d.out) % 16 == 0) &&
+                         (!d.residual || ((d.ldres % 8 == 0) && (reinterpret_cast<uintptr_t>(d.residual) % 16 == 0))) &&
+                         (!geglu || d.N % 64 == 0);
+    if (aligned && g_gemm_impl != 1) {
+        if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm2_bn<160>(d, st);
+        return launch_tapgemm2_bn<128>(d, st);
+    }
     if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm_bn<160>(d, st);
     return launch_tapgemm_bn<128>(d, st);
 }
@@ -192,6 +273,12 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<128>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<160>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+    if (const char* e = getenv("STAR_GEMM_IMPL")) g_gemm_impl = atoi(e);
     if (const char* e = getenv("STAR_ATTN_IMPL")) g_attn_impl = atoi(e);
     if (const char* e = getenv("STAR_ATTN_POLY")) g_attn_poly = atoi(e);
     STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -345,7 +432,19 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
-    const bool two_tile = g_attn_impl == 2 || (g_attn_impl == 0 && Nk > AT_BKV && Nq > AT_BQ);
+    const bool multi = Nk > AT_BKV && Nq > AT_BQ;
+    if (g_attn_impl == 3 || (g_attn_impl == 0 && multi)) {
+        dim3 grid((Nq + 255) / 256, heads, batch);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (g_attn_poly) {
+            case 4: attn3_fwd_kernel<4><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 3: attn3_fwd_kernel<3><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            default: attn3_fwd_kernel<0><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+        }
+        STAR_LAUNCH_CHECK("attn3_fwd");
+        return 0;
+    }
+    const bool two_tile = g_attn_impl == 2;
     if (two_tile) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         cudaStream_t st = (cudaStream_t)stream;

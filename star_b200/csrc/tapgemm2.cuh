@@ -1,0 +1,310 @@
+// star_b200 / csrc / tapgemm2.cuh
+// Persistent tap-GEMM (same contraction as tapgemm.cuh, see there for the tap / box addressing):
+//   * one CTA per SM loops over output tiles (n fastest, so concurrently running CTAs share the A tile in L2)
+//   * TMEM holds TWO accumulators: the epilogue of tile i runs while the MMAs of tile i+1 are issued
+//   * the epilogue is fully coalesced: residual tile arrives by TMA (prefetched during the main loop),
+//     results are staged in swizzled shared memory and leave through TMA stores (hardware clips ragged
+//     tile edges and the N tail), bias / time-embedding rows are read with 128-bit loads
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
+// warps 4-7 epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+#pragma once
+#include "common.cuh"
+#include "tapgemm.cuh"
+
+namespace star {
+
+constexpr int TG2_THREADS = 256;
+constexpr int TG2_STAGES = 4;
+
+template <int BN>
+struct TapGemm2Smem {
+    static constexpr int A_BYTES = TG_BM * TG_BK * 2;
+    static constexpr int B_BYTES = BN * TG_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int OUT_BYTES = TG_BM * BN * 2;                  // BN/32 sub-tiles of [128 rows x 64 B]
+    static constexpr int OFF_OUT = TG2_STAGES * STAGE_BYTES;
+    static constexpr int OFF_RES = OFF_OUT + OUT_BYTES;
+    static constexpr int OFF_BAR = OFF_RES + OUT_BYTES;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+STAR_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+STAR_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+STAR_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct TapGemm2Extra {
+    int num_tiles;        // m_tiles * n_tiles
+    int n_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TG2_THREADS, 1)
+tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                const __grid_constant__ TapGemmParams p, const __grid_constant__ TapGemm2Extra ex) {
+    using SM = TapGemm2Smem<BN>;
+    constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;          // TMEM columns between the two accumulators
+    constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* empty_bar = full_bar + TG2_STAGES;
+    uint64_t* acc_full = empty_bar + TG2_STAGES;     // 2
+    uint64_t* acc_empty = acc_full + 2;              // 2
+    uint64_t* res_full = acc_empty + 2;              // 1
+    uint64_t* res_empty = res_full + 1;              // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool geglu = (p.flags & TG_GEGLU) != 0;
+    const bool has_res = p.residual != nullptr;
+    const int n_per_tile = geglu ? BN / 2 : BN;
+    const int total_iters = p.ntaps * p.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_out);
+        if (has_res) tma_prefetch_desc(&tmap_res);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < TG2_STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&acc_full[b], 1);
+                mbar_init(&acc_empty[b], 128);
+            }
+            mbar_init(res_full, 1);
+            mbar_init(res_empty, 128);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_origin = [&](int tile, int* org, int& n_tile) {
+        n_tile = tile % ex.n_tiles;
+        int m_tile = tile / ex.n_tiles;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            org[i] = (m_tile % p.tiles[i]) * p.box[i];
+            m_tile /= p.tiles[i];
+        }
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)p.box_rows * 128u + (uint32_t)SM::B_BYTES;
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+                int org[4], n_tile;
+                tile_origin(tile, org, n_tile);
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int c1 = org[0] + p.tap[t][0], c2 = org[1] + p.tap[t][1];
+                    const int c3 = org[2] + p.tap[t][2], c4 = org[3] + p.tap[t][3];
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                        const int s = it % TG2_STAGES;
+                        mbar_wait(&empty_bar[s], ((it / TG2_STAGES) & 1) ^ 1);
+                        uint8_t* sa = smem + s * SM::STAGE_BYTES;
+                        uint8_t* sb = sa + SM::A_BYTES;
+                        mbar_expect_tx(&full_bar[s], tx);
+                        tma_load_5d(sa, &tmap_a, &full_bar[s], kc * TG_BK, c1, c2, c3, c4);
+                        const int kw = t * p.K + kc * TG_BK;
+                        if (!geglu) {
+                            tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * BN);
+                        } else {
+                            tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * (BN / 2));
+                            tma_load_2d(sb + (BN / 2) * 128, &tmap_w, &full_bar[s], kw, p.N + n_tile * (BN / 2));
+                        }
+                    }
+                }
+                if (has_res) {
+                    // residual tile of THIS output tile, issued after its operand loads so that waiting for the
+                    // previous epilogue to release the buffer never delays the operand prefetch
+                    const int n_base = n_tile * n_per_tile;
+                    int nsub = (p.N - n_base + 31) / 32;
+                    nsub = nsub < n_per_tile / 32 ? nsub : n_per_tile / 32;
+                    mbar_wait(res_empty, (local & 1) ^ 1);
+                    mbar_expect_tx(res_full, (uint32_t)p.box_rows * 64u * nsub);
+#pragma unroll 1
+                    for (int sb = 0; sb < nsub; ++sb)
+                        tma_load_5d(smem + SM::OFF_RES + sb * 8192, &tmap_res, res_full, n_base + sb * 32, org[0], org[1],
+                                    org[2], org[3]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(TG_BM, BN, 0, 0);
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+                const int buf = local & 1;
+                mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * ACC_STRIDE;
+                for (int i = 0; i < total_iters; ++i, ++it) {
+                    const int s = it % TG2_STAGES;
+                    mbar_wait(&full_bar[s], (it / TG2_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TG_BK / 16; ++k)
+                        umma_f16_ss(acc, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
+                                    idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue warps 4..7
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int swz = (r >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+        uint8_t* out_row = smem + SM::OFF_OUT + r * 64;
+        const uint8_t* res_row = smem + SM::OFF_RES + r * 64;
+        const bool leader = (threadIdx.x == 4 * 32);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+            int org[4], n_tile;
+            tile_origin(tile, org, n_tile);
+            const int buf = local & 1;
+            const int n_base = n_tile * n_per_tile;
+            // time-embedding row of this tile row (unet_v2v.py:684); rows of one tile may belong to different clips
+            const __half* rv_row = nullptr;
+            if (p.rowvec) {
+                int rr = r;
+                long long orow = 0, mul = 1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int l = rr % p.box[i];
+                    rr /= p.box[i];
+                    int g = org[i] + l;
+                    g = g < p.on[i] ? g : p.on[i] - 1;
+                    orow += (long long)g * mul;
+                    mul *= p.on[i];
+                }
+                rv_row = p.rowvec + (orow / p.rowvec_div) * (long long)p.N;
+            }
+            mbar_wait(&acc_full[buf], (local >> 1) & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(res_full, local & 1);
+            // previous tile's TMA stores must have finished reading the staging buffer
+            if (leader) tma_store_wait_read();
+            epi_bar_sync();
+            const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
+#pragma unroll 1
+            for (int c0 = 0; c0 < n_per_tile; c0 += 32) {
+                uint32_t v[32];
+                float f[32];
+                tmem_ld32(t_row + c0, v);
+                const int n0 = n_base + c0;
+                if (geglu) {
+                    uint32_t g[32];
+                    tmem_ld32(t_row + (BN / 2) + c0, g);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float bv[8], bg[8];
+                        const bool inb = (n0 + u * 8 + 8 <= p.N) && p.bias;
+                        if (inb) {
+                            unpack8h(__ldg(reinterpret_cast<const uint4*>(p.bias + n0 + u * 8)), bv);
+                            unpack8h(__ldg(reinterpret_cast<const uint4*>(p.bias + p.N + n0 + u * 8)), bg);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float xv = __uint_as_float(v[u * 8 + e]), gv = __uint_as_float(g[u * 8 + e]);
+                            if (inb) { xv += bv[e]; gv += bg[e]; }
+                            f[u * 8 + e] = xv * gelu_erf_f(gv);
+                        }
+                    }
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float bv[8];
+                        const bool inb = (n0 + u * 8 + 8 <= p.N) && p.bias;
+                        if (inb) unpack8h(__ldg(reinterpret_cast<const uint4*>(p.bias + n0 + u * 8)), bv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[u * 8 + e] = __uint_as_float(v[u * 8 + e]) + (inb ? bv[e] : 0.f);
+                    }
+                }
+                if (c0 + 32 >= n_per_tile) {                 // last TMEM read of this accumulator: hand it back
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                if (rv_row) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (n0 + u * 8 + 8 <= p.N) {
+                            float tv[8];
+                            unpack8h(__ldg(reinterpret_cast<const uint4*>(rv_row + n0 + u * 8)), tv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[u * 8 + e] += tv[e];
+                        }
+                    }
+                }
+                const int sub = c0 >> 5;
+                if (has_res) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float rv[8];
+                        unpack8h(*reinterpret_cast<const uint4*>(res_row + sub * 8192 + ((u ^ swz) * 16)), rv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[u * 8 + e] += rv[e];
+                    }
+                }
+                if (p.flags & TG_SILU_OUT) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 o;
+                    o.x = pack_half2(f[u * 8 + 0], f[u * 8 + 1]);
+                    o.y = pack_half2(f[u * 8 + 2], f[u * 8 + 3]);
+                    o.z = pack_half2(f[u * 8 + 4], f[u * 8 + 5]);
+                    o.w = pack_half2(f[u * 8 + 6], f[u * 8 + 7]);
+                    *reinterpret_cast<uint4*>(out_row + sub * 8192 + ((u ^ swz) * 16)) = o;
+                }
+            }
+            if (has_res) mbar_arrive(res_empty);
+            fence_proxy_async_smem();
+            epi_bar_sync();
+            if (leader) {
+#pragma unroll 1
+                for (int sb = 0; sb < n_per_tile / 32; ++sb) {
+                    if (n_base + sb * 32 < p.N)
+                        tma_store_5d(&tmap_out, smem + SM::OFF_OUT + sb * 8192, n_base + sb * 32, org[0], org[1], org[2], org[3]);
+                }
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_all();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace star
