@@ -1,0 +1,269 @@
+// star_b200 / csrc / attn4.cuh
+// Fourth-generation spatial-attention kernel (head_dim 64): attn2's structure (two 128-row query tiles
+// per CTA sharing every K/V tile, thread = query row, single-pass softmax from TMEM, lazy max, O
+// accumulated in TMEM) with the probabilities kept in TENSOR MEMORY:
+//   * P_t(j) is written with tcgen05.st as packed fp16 pairs (64 columns per tile) and the PV MMA takes
+//     its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  The ncu capture of attn2
+//     (profiles/r01_ncu_attn2.txt) showed neither MUFU (54 %) nor issue slots (43 %) saturated; the
+//     shared-memory port was: per KV tile the SS formulation moves 256 KB through smem (Q, K, V operand
+//     reads, P written by threads and read back as the A operand, TMA fills) = 2048 clk at 128 B/clk,
+//     twice the MMA time.  Keeping P out of smem halves that.
+//   * the MMA thread issues both S(j+1) before waiting for either P(j) (no head-of-line blocking).
+//   * the 64 KB of smem freed by P deepen the K/V ring to 5 stages.
+// TMEM columns: S[t] t*128, O[t] 256 + t*64, P[t] 384 + t*64.
+#pragma once
+#include "common.cuh"
+#include "attn.cuh"
+#include "attn2.cuh"
+
+namespace star {
+
+constexpr int A4_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle (one warpgroup, registers donated); 4-7 / 8-11: softmax
+constexpr int A4_KV_STAGES = 5;
+
+struct Attn4Smem {
+    static constexpr int TILE = 128 * 64 * 2;                 // 16 KB
+    static constexpr int OFF_Q = 0;                           // 2 tiles
+    static constexpr int OFF_K = OFF_Q + 2 * TILE;
+    static constexpr int OFF_V = OFF_K + A4_KV_STAGES * TILE;
+    static constexpr int OFF_BAR = OFF_V + A4_KV_STAGES * TILE;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+template <int POLY_EVERY>      // every POLY_EVERY-th exponential uses ex2_poly (0 = never)
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Attn4Smem::OFF_BAR);
+    uint64_t* q_full = bars;                 // 1
+    uint64_t* kv_full = bars + 1;            // 5
+    uint64_t* kv_empty = bars + 6;           // 5
+    uint64_t* s_full = bars + 11;            // 2   MMA -> softmax WG t : S_t(j) complete
+    uint64_t* s_free = bars + 13;            // 2   softmax WG t -> MMA : S_t(j) is in registers
+    uint64_t* p_full = bars + 15;            // 2   softmax WG t -> MMA : P_t(j) in TMEM, O_t rescaled
+    uint64_t* pv_done = bars + 17;           // 2   MMA -> softmax WG t : O_t += P_t(j) V_j retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256;
+    const int head = blockIdx.y;
+    const int batch = blockIdx.z;
+    const int kv_batch = batch / p.kv_batch_div;
+    const int nt = (p.Nk + 127) / 128;
+    const int ntq = (q0 + 128 < p.Nq) ? 2 : 1;          // second query tile may be empty
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int s = 0; s < A4_KV_STAGES; ++s) {
+                mbar_init(&kv_full[s], 1);
+                mbar_init(&kv_empty[s], 1);
+            }
+            for (int t = 0; t < 2; ++t) {
+                mbar_init(&s_full[t], 1);
+                mbar_init(&s_free[t], 128);
+                mbar_init(&p_full[t], 128);
+                mbar_init(&pv_done[t], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;      // S[t] at cols t*128, O[t] at cols 256 + t*64
+
+    if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (lane == 0) {
+            mbar_expect_tx(q_full, ntq * Attn4Smem::TILE);
+            for (int t = 0; t < ntq; ++t)
+                tma_load_3d(smem + Attn4Smem::OFF_Q + t * Attn4Smem::TILE, &tmap_q, q_full, head * 64, q0 + t * 128, batch);
+            for (int j = 0; j < nt; ++j) {
+                const int s = j % A4_KV_STAGES;
+                mbar_wait(&kv_empty[s], ((j / A4_KV_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], 2 * Attn4Smem::TILE);
+                tma_load_3d(smem + Attn4Smem::OFF_K + s * Attn4Smem::TILE, &tmap_k, &kv_full[s], head * 64, j * 128, kv_batch);
+                tma_load_3d(smem + Attn4Smem::OFF_V + s * Attn4Smem::TILE, &tmap_v, &kv_full[s], head * 64, j * 128, kv_batch);
+            }
+        }
+    } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t q_addr = smem_u32(smem + Attn4Smem::OFF_Q + t * Attn4Smem::TILE);
+                const uint32_t k_addr = smem_u32(smem + Attn4Smem::OFF_K + (j % A4_KV_STAGES) * Attn4Smem::TILE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base + t * 128, umma_desc_sw128(q_addr + k * 32, 16, 1024),
+                                umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[t]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            for (int t = 0; t < ntq; ++t) issue_s(t, 0);
+            for (int j = 0; j < nt; ++j) {
+                const int st = j % A4_KV_STAGES;
+                if (j + 1 < nt) {                       // scores of the next KV tile for both query tiles first
+                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                    for (int t = 0; t < ntq; ++t) {
+                        mbar_wait(&s_free[t], j & 1);
+                        tc_fence_after();
+                        issue_s(t, j + 1);
+                    }
+                }
+                for (int t = 0; t < ntq; ++t) {
+                    mbar_wait(&p_full[t], j & 1);
+                    tc_fence_after();
+                    const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + st * Attn4Smem::TILE);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)         // A = P_t (TMEM, 8 columns = 16 fp16 keys per step), B = V (MN-major)
+                        umma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
+                                    umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&pv_done[t]);
+                }
+                umma_commit(&kv_empty[st]);
+            }
+        }
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int t = (warp - 4) >> 2;                   // query tile of this warpgroup
+        if (t < ntq) {
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            const uint32_t t_s = tmem_base + t * 128 + lane_off;
+            const uint32_t t_o = tmem_base + 256 + t * 64 + lane_off;
+            const uint32_t t_p = tmem_base + 384 + t * 64 + lane_off;
+            const float sl2 = p.scale_log2;
+            float m_used = 0.f, l_run = 0.f;
+
+            for (int j = 0; j < nt; ++j) {
+                const int kbase = j * 128;
+                const bool tail = (kbase + 128 > p.Nk);
+                mbar_wait(&s_full[t], j & 1);
+                tc_fence_after();
+                uint32_t v[128];
+                tmem_ld32(t_s, v);
+                tmem_ld32(t_s + 32, v + 32);
+                tmem_ld32(t_s + 64, v + 64);
+                tmem_ld32(t_s + 96, v + 96);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_free[t]);                 // S_t may be overwritten by S_t(j+1)
+
+                float mx = -INFINITY;
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i)
+                        if (kbase + i >= p.Nk) v[i] = 0xff800000u;      // -inf
+                }
+#pragma unroll
+                for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                const float mc = mx * sl2;
+                float factor = 1.f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mc;
+                } else if (mc > m_used + 8.0f) {
+                    factor = ex2_approx(m_used - mc);
+                    m_used = mc;
+                    need = true;
+                }
+                if (j > 0) {
+                    mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, need)) {
+                        uint32_t o[32];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            tmem_ld32(t_o + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                            tmem_st32(t_o + c * 32, o);
+                        }
+                        tmem_st_wait();
+                        l_run *= factor;
+                    }
+                }
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {            // 2 x 64 probabilities -> 32 packed columns each
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int i = hh * 64 + e * 2;
+                        const float x0 = fmaf(__uint_as_float(v[i]), sl2, -m_used);
+                        const float x1 = fmaf(__uint_as_float(v[i + 1]), sl2, -m_used);
+                        float p0, p1;
+                        if (POLY_EVERY > 0 && ((i >> 1) % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == POLY_EVERY - 1) {
+                            p0 = ex2_poly(x0);
+                            p1 = ex2_poly(x1);
+                        } else {
+                            p0 = ex2_approx(x0);
+                            p1 = ex2_approx(x1);
+                        }
+                        if ((e & 3) == 0) l0 += p0 + p1;
+                        else if ((e & 3) == 1) l1 += p0 + p1;
+                        else if ((e & 3) == 2) l2 += p0 + p1;
+                        else l3 += p0 + p1;
+                        pk[e] = pack_half2(p0, p1);
+                    }
+                    tmem_st32(t_p + hh * 32, pk);
+                }
+                tmem_st_wait();
+                const float l_part = (l0 + l1) + (l2 + l3);
+                tc_fence_before();
+                mbar_arrive(&p_full[t]);
+                l_run += l_part;
+            }
+            // epilogue: O / l -> fp16
+            mbar_wait(&pv_done[t], (nt - 1) & 1);
+            tc_fence_after();
+            const int q = q0 + t * 128 + r;
+            const float inv = 1.0f / l_run;
+            __half* op = p.out + ((long long)batch * p.Nq + q) * p.ldo + head * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld32(t_o + c * 32, o);
+                tmem_ld_wait();
+                if (q < p.Nq) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 w;
+                        w.x = pack_half2(__uint_as_float(o[u * 8 + 0]) * inv, __uint_as_float(o[u * 8 + 1]) * inv);
+                        w.y = pack_half2(__uint_as_float(o[u * 8 + 2]) * inv, __uint_as_float(o[u * 8 + 3]) * inv);
+                        w.z = pack_half2(__uint_as_float(o[u * 8 + 4]) * inv, __uint_as_float(o[u * 8 + 5]) * inv);
+                        w.w = pack_half2(__uint_as_float(o[u * 8 + 6]) * inv, __uint_as_float(o[u * 8 + 7]) * inv);
+                        reinterpret_cast<uint4*>(op + c * 32)[u] = w;
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace star

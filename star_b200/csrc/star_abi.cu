@@ -15,6 +15,7 @@
 #include "attn.cuh"
 #include "attn2.cuh"
 #include "attn3.cuh"
+#include "attn4.cuh"
 #include "rowops.cuh"
 #include "tapgemm.cuh"
 #include "tapgemm2.cuh"
@@ -275,6 +276,9 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<128>::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<160>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
@@ -433,7 +437,18 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.out = (__half*)O; p.ldo = ldo;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
     const bool multi = Nk > AT_BKV && Nq > AT_BQ;
-    if (g_attn_impl == 3 || (g_attn_impl == 0 && multi)) {
+    if (g_attn_impl == 4 || (g_attn_impl == 0 && multi)) {
+        dim3 grid((Nq + 255) / 256, heads, batch);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (g_attn_poly) {
+            case 4: attn4_fwd_kernel<4><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 3: attn4_fwd_kernel<3><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            default: attn4_fwd_kernel<0><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+        }
+        STAR_LAUNCH_CHECK("attn4_fwd");
+        return 0;
+    }
+    if (g_attn_impl == 3) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         cudaStream_t st = (cudaStream_t)stream;
         switch (g_attn_poly) {
