@@ -318,7 +318,15 @@ def main():
             f.write(f"# per-op device time inside the timed region ({args.steps} solver steps, CUDA events)\n")
             for k, v in sorted(per_op.items(), key=lambda kv: -kv[1]):
                 f.write(f"{k:24s} {v:12.3f} ms  {100 * v / tot:6.2f} %\n")
-            f.write(f"total traced {tot:.3f} ms; wall (events) {ms:.3f} ms\n")
+            f.write(f"total traced {tot:.3f} ms; wall (events) {ms:.3f} ms\n\n# top (op, signature) groups\n")
+            groups = {}
+            for name, sig, t_ms in trace:
+                key = (name, tuple(x for x in sig if not isinstance(x, float)))
+                g = groups.setdefault(key, [0, 0.0])
+                g[0] += 1
+                g[1] += t_ms
+            for (name, sig), (cnt, t_ms) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:40]:
+                f.write(f"{name:20s} x{cnt:4d} {t_ms:10.3f} ms {100 * t_ms / tot:6.2f} %  {sig}\n")
 
     # ---- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample ---------------
     cpu = None
