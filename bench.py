@@ -44,7 +44,6 @@ def parse():
     ap.add_argument("--lat-w", type=int, default=LAT_W)
     ap.add_argument("--frames", type=int, default=0, help="override clip length (default 32, or 16(N+1) for N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--trace-out", default="", help="write the per-op time table of the timed region to this file")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; not a valid bench line)")
     return ap.parse_args()
@@ -137,18 +136,61 @@ class _StubText:
 
 
 # ---------------------------------------------------------------------------------- CPU reference arm
-def cpu_forward_time(sd_cpu, kw, frames, H, W, repeats=1, warm=0):
-    """seconds for ONE oracle forward (fp32, all host threads) on `frames` frames at latent HxW."""
+# The reference's CPU path is ~1e4 x slower than the GPU path (one fp32 forward of ONE frame at latent 122x216
+# takes ~220 s on 128 host cores), so it is timed on a bounded sample -- 1 frame at latent 34x64 -- and
+# extrapolated by ALGORITHMIC FLOPs counted with the same counter (torch.utils.flop_counter) on the sample and,
+# on meta tensors, on the full workload: frames/s = frames / (steps * flops_full_step / measured_flop_rate).
+CPU_SAMPLE = (1, 34, 64)         # frames, latent H (2 mod 8), latent W (0 mod 8)
+
+
+def oracle_flops(kw, frames, H, W):
+    """algorithmic FLOPs (2*MAC, attention 4*Nq*Nk*d) of ONE oracle forward, counted on meta tensors"""
+    from torch.utils.flop_counter import FlopCounterMode
     from oracle.unet_ref import UNetCfg, controlled_unet_forward
-    feat, y, _ = synth_inputs(frames, H, W, seed=1)
-    x = torch.randn(1, 4, frames, H, W)
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**kw)
+        sd = {k: torch.empty(v.shape) for k, v in net.state_dict().items()}
+        x = torch.empty(1, 4, frames, H, W)
+        y = torch.empty(1, 77, 1024)
+        t = torch.zeros(1, dtype=torch.long)
+    with FlopCounterMode(display=False) as fc:
+        controlled_unet_forward(sd, x, t, y, x, UNetCfg(**kw))
+    return float(fc.get_total_flops())
+
+
+def cpu_sample_setup(kw):
+    from star_b200.utils.synth import synth_state_dict
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**kw)
+    return synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=2)
+
+
+def cpu_step_fn(sd, kw, sample):
+    from oracle.unet_ref import UNetCfg, controlled_unet_forward
+    fs, H, W = sample
+    feat, y, ny = synth_inputs(fs, H, W, seed=1)
+    x = torch.randn(1, 4, fs, H, W)
     t = torch.tensor([899])
-    for _ in range(warm):
-        controlled_unet_forward(sd_cpu, x, t, y, feat, UNetCfg(**kw))
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        controlled_unet_forward(sd_cpu, x, t, y, feat, UNetCfg(**kw))
-    return (time.perf_counter() - t0) / repeats
+
+    def step():                      # one solver step on the sample: 2 CFG forwards + guidance combine
+        a = controlled_unet_forward(sd, x, t, y, feat, UNetCfg(**kw))
+        b = controlled_unet_forward(sd, x, t, ny, feat, UNetCfg(**kw))
+        return b + 7.5 * (a - b)
+    return step
+
+
+def cpu_extrapolate(dt_step, kw, sample, H, W):
+    """seconds per solver step on the sample -> frames/s of the full CHUNK-frame, HxW workload"""
+    f_sample = 2.0 * oracle_flops(kw, *sample)
+    f_full = 2.0 * oracle_flops(kw, CHUNK, H, W)
+    rate = f_sample / dt_step                                   # FLOP/s the host sustains on this path
+    value = CHUNK / (SCHEDULE_STEPS * f_full / rate)
+    note = (f"sample = one solver step (2 CFG forwards) of {sample[0]} frame(s) at latent {sample[1]}x{sample[2]}, fp32: "
+            f"{dt_step:.2f} s = {rate / 1e12:.3f} TFLOP/s; full step = {f_full / 1e12:.1f} TFLOP "
+            f"({CHUNK} frames, latent {H}x{W}); extrapolated by algorithmic FLOPs")
+    return value, note
 
 
 def run_reference(args):
@@ -156,42 +198,27 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from star_b200.utils.synth import synth_state_dict
-    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
-    from oracle.unet_ref import UNetCfg, controlled_unet_forward
     torch.set_num_threads(os.cpu_count() or 1)
     kw = dict(dim_mult=[1, 2, 1, 4], num_res_blocks=1) if args.small else {}
-    with torch.device("meta"):
-        net = ControlledV2VUNet(**kw)
-    sd = synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=2)
-    fs, H, W = args.cpu_sample_frames, args.lat_h, args.lat_w
-    feat, y, ny = synth_inputs(fs, H, W, seed=1)
-    x = torch.randn(1, 4, fs, H, W)
-    t = torch.tensor([899])
-
-    def step():                      # one solver step on the sample: 2 CFG forwards + guidance
-        a = controlled_unet_forward(sd, x, t, y, feat, UNetCfg(**kw))
-        b = controlled_unet_forward(sd, x, t, ny, feat, UNetCfg(**kw))
-        return b + 7.5 * (a - b)
-
+    sd = cpu_sample_setup(kw)
+    step = cpu_step_fn(sd, kw, CPU_SAMPLE)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = fs / (SCHEDULE_STEPS * dt)
-    sample = (f"{fs} frame(s) of the {CHUNK}-frame chunk at latent {H}x{W}, fp32, one solver step = 2 CFG forwards "
-              f"(per-frame cost of the {CHUNK}-frame chunk extrapolated linearly in frames)")
+    value, note = cpu_extrapolate(dt, kw, CPU_SAMPLE, args.lat_h, args.lat_w)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"I2VGen-XL light-deg 4x 240p->960p, {CHUNK}-frame chunk, latent {H}x{W}, 50 steps, CFG 7.5",
+        "config": {"workload": f"I2VGen-XL light-deg 4x 240p->960p, {CHUNK}-frame chunk, latent {args.lat_h}x{args.lat_w}, "
+                               "50 steps, CFG 7.5",
                    "model": "ControlledV2VUNet" + (" (reduced)" if args.small else " 2.04B params"),
-                   "parallelism": "cpu"},
+                   "parallelism": "cpu", "step": "one solver step (2 CFG forwards) on the bounded sample"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+                         "sample": note},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -334,12 +361,12 @@ def main():
         del pipe, net
         torch.cuda.empty_cache()
         torch.set_num_threads(os.cpu_count() or 1)
-        fs = args.cpu_sample_frames
-        t_fwd = cpu_forward_time(sd_cpu, kw, fs, H, W)
-        cpu_val = fs / (SCHEDULE_STEPS * 2 * t_fwd)
-        cpu = {"value": cpu_val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 oracle forward (fp32) on {fs} frame(s) at latent {H}x{W}: {t_fwd:.1f} s; "
-                         f"x2 CFG forwards x50 steps, linear in frames"}
+        step = cpu_step_fn(sd_cpu, kw, CPU_SAMPLE)
+        step()
+        t0 = time.perf_counter()
+        step()
+        cpu_val, note = cpu_extrapolate(time.perf_counter() - t0, kw, CPU_SAMPLE, H, W)
+        cpu = {"value": cpu_val, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": note}
 
     if rank == 0:
         line = {

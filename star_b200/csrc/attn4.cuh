@@ -115,28 +115,39 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
             for (int t = 0; t < ntq; ++t) issue_s(t, 0);
-            for (int j = 0; j < nt; ++j) {
-                const int st = j % A4_KV_STAGES;
-                if (j + 1 < nt) {                       // scores of the next KV tile for both query tiles first
-                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
-                    for (int t = 0; t < ntq; ++t) {
-                        mbar_wait(&s_free[t], j & 1);
-                        tc_fence_after();
-                        issue_s(t, j + 1);
-                    }
-                }
-                for (int t = 0; t < ntq; ++t) {
-                    mbar_wait(&p_full[t], j & 1);
-                    tc_fence_after();
-                    const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + st * Attn4Smem::TILE);
+            auto issue_pv = [&](int t, int j) {
+                mbar_wait(&p_full[t], j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + (j % A4_KV_STAGES) * Attn4Smem::TILE);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)         // A = P_t (TMEM, 8 columns = 16 fp16 keys per step), B = V (MN-major)
-                        umma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
-                                    umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&pv_done[t]);
+                for (int k = 0; k < 8; ++k)             // A = P_t (TMEM, 8 columns = 16 fp16 keys per step), B = V (MN-major)
+                    umma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
+                                umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&pv_done[t]);
+            };
+            auto next_s = [&](int t, int j) {           // S_t(j+1) as soon as S_t(j) sits in the softmax registers
+                mbar_wait(&s_free[t], j & 1);
+                tc_fence_after();
+                issue_s(t, j + 1);
+            };
+            // Issue order = event order of two softmax groups running half a period apart:
+            //   S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)     (the ncu capture of the first attn4 showed the groups
+            //   waiting ~25 % of their time for PV(j-1), queued behind both S(j+1), profiles/r01_ncu_attn4.txt)
+            for (int j = 0; j < nt; ++j) {
+                const bool more = (j + 1 < nt);
+                if (more) {
+                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                    next_s(0, j);
                 }
-                umma_commit(&kv_empty[st]);
+                if (j > 0) {
+                    if (ntq > 1) issue_pv(1, j - 1);
+                    umma_commit(&kv_empty[(j - 1) % A4_KV_STAGES]);
+                }
+                if (more && ntq > 1) next_s(1, j);
+                issue_pv(0, j);
             }
+            if (ntq > 1) issue_pv(1, nt - 1);
+            umma_commit(&kv_empty[(nt - 1) % A4_KV_STAGES]);
         }
     } else if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");

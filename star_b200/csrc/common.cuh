@@ -177,8 +177,22 @@ STAR_DEVINL void umma_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------- misc math
+STAR_DEVINL float ex2_approx(float x);
 STAR_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-STAR_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact (erf) GELU, nn.GELU() default (unet_v2v.py:504).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
+// below the fp16 rounding of the result): 2 MUFU + ~12 FMA-pipe ops instead of libdevice erff's ~30.
+STAR_DEVINL float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = ex2_approx(-1.4426950408889634f * ax * ax);
+    const float r = fmaf(-poly * t, e, 1.0f);
+    return copysignf(r, x);
+}
+STAR_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 STAR_DEVINL float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 STAR_DEVINL uint32_t pack_half2(float a, float b) {

@@ -141,7 +141,20 @@ gn_stats_kernel(const __half* __restrict__ x, double* __restrict__ stats, long l
         for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
         const bool active = (oc < O) && (ln < lanes);
         if (active) {
-            for (long long r = r0 + ln; r < r1; r += lanes) {
+            long long r = r0 + ln;
+            for (; r + 3ll * lanes < r1; r += 4ll * lanes) {          // 4 independent 16-byte loads in flight
+                uint4 u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + (long long)k * lanes) * C + oc * 8));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float f[8];
+                    unpack8(u[k], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+                }
+            }
+            for (; r < r1; r += lanes) {
                 float f[8];
                 unpack8(__ldg(reinterpret_cast<const uint4*>(xs + r * C + oc * 8)), f);
 #pragma unroll
@@ -197,12 +210,13 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
                                 long long rows_per_sample, long long total_rows, int C, int silu) {
     const int O = C / 8;
     const long long n = total_rows * O;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto apply = [&](long long i, const uint4& raw) {
         const long long row = i / O;
         const int oc = (int)(i % O);
         const long long sample = row / rows_per_sample;
         float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+        unpack8(raw, f);
         const float4* abp = reinterpret_cast<const float4*>(ab + (sample * C + oc * 8) * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -212,8 +226,17 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
             f[2 * j] = y0;
             f[2 * j + 1] = y1;
         }
-        *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(f);
+        reinterpret_cast<uint4*>(out)[i] = pack8(f);
+    };
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {                      // 4 independent 16-byte loads in flight
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x) + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) apply(i + k * stride, u[k]);
     }
+    for (; i < n; i += stride) apply(i, __ldg(reinterpret_cast<const uint4*>(x) + i));
 }
 
 // ------------------------------------------------------------------ LayerNorm over C with fused LIEM gate
@@ -222,71 +245,95 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
 // gate_mode 2: y = LN(x * sigmoid(w0*max_c(x) + w1*mean_c(x)))   temporal LIEM (unet_v2v.py:402-411, :481-487)
 // One warp per row; the row lives in registers (C <= 1280 -> <= 5 x 8 values per lane).
 constexpr int LN_MAX_OCT = 5;
+template <int LN_OCT>          // 16-byte column groups per lane: 2 (C <= 512), 3 (C <= 768), 5 (C <= 1280)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                  __half* __restrict__ out, long long rows, int C, float eps, int gate_mode,
                  const __half* __restrict__ gate, float w0, float w1) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int O = C / 8;
-    float v[LN_MAX_OCT][8];
-    float s = 0.f, mx = -INFINITY;
+    // affine parameters stay in registers for all rows of this warp
+    uint4 gm_u[LN_OCT], bt_u[LN_OCT], cur[LN_OCT], nxt[LN_OCT];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_OCT; ++i) {
+    for (int i = 0; i < LN_OCT; ++i) {
         const int oc = lane + 32 * i;
         if (oc < O) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), v[i]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s += v[i][j]; mx = fmaxf(mx, v[i][j]); }
+            gm_u[i] = __ldg(reinterpret_cast<const uint4*>(gamma + oc * 8));
+            bt_u[i] = __ldg(reinterpret_cast<const uint4*>(beta + oc * 8));
+            cur[i] = __ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8));
         }
     }
-    if (gate_mode != 0) {
-        float g;
-        if (gate_mode == 1) {
-            g = __half2float(gate[row]);
-        } else {
-            s = warp_sum(s);
-            mx = warp_max(mx);
-            // reference computes max / mean / Linear(2->1) / sigmoid in fp16 (autocast keeps input dtype)
-            const float mean_h = __half2float(__float2half_rn(s / (float)C));
-            const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
-            g = __half2float(__float2half_rn(sigmoid_f(lin)));
-        }
-        s = 0.f;
+    for (; row < rows; row += nwarps) {
+        const long long nrow = row + nwarps;
+        if (nrow < rows) {                              // prefetch the next row of this warp
 #pragma unroll
-        for (int i = 0; i < LN_MAX_OCT; ++i) {
+            for (int i = 0; i < LN_OCT; ++i) {
+                const int oc = lane + 32 * i;
+                if (oc < O) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + nrow * C + oc * 8));
+            }
+        }
+        float v[LN_OCT][8];
+        float s = 0.f, mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < LN_OCT; ++i) {
             const int oc = lane + 32 * i;
             if (oc < O) {
+                unpack8(cur[i], v[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[i][j] = __half2float(__float2half_rn(v[i][j] * g));     // fp16 product, as the reference
-                    s += v[i][j];
+                for (int j = 0; j < 8; ++j) { s += v[i][j]; mx = fmaxf(mx, v[i][j]); }
+            }
+        }
+        if (gate_mode != 0) {
+            float g;
+            if (gate_mode == 1) {
+                g = __half2float(gate[row]);
+            } else {
+                s = warp_sum(s);
+                mx = warp_max(mx);
+                // reference computes max / mean / Linear(2->1) / sigmoid in fp16 (autocast keeps input dtype)
+                const float mean_h = __half2float(__float2half_rn(s / (float)C));
+                const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
+                g = __half2float(__float2half_rn(sigmoid_f(lin)));
+            }
+            s = 0.f;
+#pragma unroll
+            for (int i = 0; i < LN_OCT; ++i) {
+                const int oc = lane + 32 * i;
+                if (oc < O) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[i][j] = __half2float(__float2half_rn(v[i][j] * g));     // fp16 product, as the reference
+                        s += v[i][j];
+                    }
                 }
             }
         }
-    }
-    const float mean = warp_sum(s) / (float)C;
-    float var = 0.f;
+        const float mean = warp_sum(s) / (float)C;
+        float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_OCT; ++i) {
-        const int oc = lane + 32 * i;
-        if (oc < O) {
+        for (int i = 0; i < LN_OCT; ++i) {
+            const int oc = lane + 32 * i;
+            if (oc < O) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var = fmaf(d, d, var); }
+                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var = fmaf(d, d, var); }
+            }
         }
-    }
-    const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+        const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_OCT; ++i) {
-        const int oc = lane + 32 * i;
-        if (oc < O) {
-            float gm[8], bt[8], y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + oc * 8)), gm);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(beta + oc * 8)), bt);
+        for (int i = 0; i < LN_OCT; ++i) {
+            const int oc = lane + 32 * i;
+            if (oc < O) {
+                float gm[8], bt[8], y[8];
+                unpack8(gm_u[i], gm);
+                unpack8(bt_u[i], bt);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
-            *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(y);
+                for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+                *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(y);
+                cur[i] = nxt[i];
+            }
         }
     }
 }
@@ -296,21 +343,22 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
 __global__ void __launch_bounds__(256)
 liem_reduce_kernel(const __half* __restrict__ x, __half* __restrict__ mm, long long rows, int C) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int O = C / 8;
-    float s = 0.f, mx = -INFINITY;
-    for (int oc = lane; oc < O; oc += 32) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+        float s = 0.f, mx = -INFINITY;
+        for (int oc = lane; oc < O; oc += 32) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s += f[j]; mx = fmaxf(mx, f[j]); }
-    }
-    s = warp_sum(s);
-    mx = warp_max(mx);
-    if (lane == 0) {
-        __half2 h = __floats2half2_rn(mx, s / (float)C);
-        *reinterpret_cast<__half2*>(mm + row * 2) = h;
+            for (int j = 0; j < 8; ++j) { s += f[j]; mx = fmaxf(mx, f[j]); }
+        }
+        s = warp_sum(s);
+        mx = warp_max(mx);
+        if (lane == 0) {
+            __half2 h = __floats2half2_rn(mx, s / (float)C);
+            *reinterpret_cast<__half2*>(mm + row * 2) = h;
+        }
     }
 }
 // step 2: 7x7 conv (2 -> 1, pad 3, no bias) + sigmoid -> gate[R] fp16.  wt = conv1.weight[0] as [2][7][7]

@@ -214,7 +214,8 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
         tr = to;
     }
     const int grid = (int)std::min<long long>(total, g_num_sms);
-    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::TOTAL, st>>>(ta, tw, to, tr, p, ex);
+    ex.stages = TapGemm2Smem<BN>::stages(d.residual != nullptr);
+    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
     return 0;
 }
@@ -274,8 +275,8 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<128>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Smem<160>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true))));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
@@ -521,9 +522,17 @@ int star_layernorm(const void* X, const void* gamma, const void* beta, void* out
                    int gate_mode, const void* gate, float w0, float w1, void* stream) {
     if (C % 8 || C / 8 > 32 * LN_MAX_OCT) return fail("star_layernorm: unsupported C=%d", C);
     const int wpb = 8;
-    layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const __half*)X, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, C, eps, gate_mode,
-        (const __half*)gate, w0, w1);
+    const long long want = (rows + wpb - 1) / wpb;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 16);
+    const int oct = (C / 8 + 31) / 32;
+#define STAR_LN_LAUNCH(N)                                                                                          \
+    layernorm_kernel<N><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma,          \
+                                                                     (const __half*)beta, (__half*)out, rows, C, eps, \
+                                                                     gate_mode, (const __half*)gate, w0, w1)
+    if (oct <= 2) STAR_LN_LAUNCH(2);
+    else if (oct <= 3) STAR_LN_LAUNCH(3);
+    else STAR_LN_LAUNCH(5);
+#undef STAR_LN_LAUNCH
     STAR_LAUNCH_CHECK("layernorm");
     return 0;
 }
@@ -533,7 +542,7 @@ int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* ga
     if (C % 8) return fail("star_liem_spatial_gate: C must be a multiple of 8");
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)BT * H * W;
-    liem_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)X, (__half*)mm_ws, rows, C);
+    liem_reduce_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, (long long)g_num_sms * 8), 256, 0, st>>>((const __half*)X, (__half*)mm_ws, rows, C);
     STAR_LAUNCH_CHECK("liem_reduce");
     liem_conv7_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __half*)mm_ws, (const __half*)w98, (__half*)gate,
                                                                        BT, H, W);

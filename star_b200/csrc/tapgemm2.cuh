@@ -14,7 +14,7 @@
 namespace star {
 
 constexpr int TG2_THREADS = 256;
-constexpr int TG2_STAGES = 4;
+constexpr int TG2_MAX_STAGES = 6;
 
 template <int BN>
 struct TapGemm2Smem {
@@ -22,10 +22,13 @@ struct TapGemm2Smem {
     static constexpr int B_BYTES = BN * TG_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BYTES = TG_BM * BN * 2;                  // BN/32 sub-tiles of [128 rows x 64 B]
-    static constexpr int OFF_OUT = TG2_STAGES * STAGE_BYTES;
-    static constexpr int OFF_RES = OFF_OUT + OUT_BYTES;
-    static constexpr int OFF_BAR = OFF_RES + OUT_BYTES;
-    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+    static constexpr int BUDGET = 232448 - 1024 - 256;                // 227 KB minus alignment slack and barriers
+    // as many operand stages as fit beside the staging buffer (and the residual buffer when there is one)
+    static constexpr int stages(bool has_res) {
+        int n = (BUDGET - OUT_BYTES * (has_res ? 2 : 1)) / STAGE_BYTES;
+        return n > TG2_MAX_STAGES ? TG2_MAX_STAGES : n;
+    }
+    static constexpr int total(bool has_res) { return stages(has_res) * STAGE_BYTES + OUT_BYTES * (has_res ? 2 : 1) + 256 + 1024; }
 };
 
 STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
@@ -41,6 +44,7 @@ STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory");
 struct TapGemm2Extra {
     int num_tiles;        // m_tiles * n_tiles
     int n_tiles;
+    int stages;           // operand ring depth (depends on BN and on whether a residual buffer is needed)
 };
 
 template <int BN>
@@ -53,9 +57,13 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
-    uint64_t* empty_bar = full_bar + TG2_STAGES;
-    uint64_t* acc_full = empty_bar + TG2_STAGES;     // 2
+    const int NS = ex.stages;
+    const int OFF_OUT = NS * SM::STAGE_BYTES;
+    const int OFF_RES = OFF_OUT + SM::OUT_BYTES;
+    const int OFF_BAR = OFF_OUT + SM::OUT_BYTES * (p.residual ? 2 : 1);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty_bar = full_bar + TG2_MAX_STAGES;
+    uint64_t* acc_full = empty_bar + TG2_MAX_STAGES; // 2
     uint64_t* acc_empty = acc_full + 2;              // 2
     uint64_t* res_full = acc_empty + 2;              // 1
     uint64_t* res_empty = res_full + 1;              // 1
@@ -76,7 +84,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < TG2_STAGES; ++s) {
+            for (int s = 0; s < NS; ++s) {
                 mbar_init(&full_bar[s], 1);
                 mbar_init(&empty_bar[s], 1);
             }
@@ -118,8 +126,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int c1 = org[0] + p.tap[t][0], c2 = org[1] + p.tap[t][1];
                     const int c3 = org[2] + p.tap[t][2], c4 = org[3] + p.tap[t][3];
                     for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                        const int s = it % TG2_STAGES;
-                        mbar_wait(&empty_bar[s], ((it / TG2_STAGES) & 1) ^ 1);
+                        const int s = it % NS;
+                        mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
                         uint8_t* sa = smem + s * SM::STAGE_BYTES;
                         uint8_t* sb = sa + SM::A_BYTES;
                         mbar_expect_tx(&full_bar[s], tx);
@@ -143,7 +151,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     mbar_expect_tx(res_full, (uint32_t)p.box_rows * 64u * nsub);
 #pragma unroll 1
                     for (int sb = 0; sb < nsub; ++sb)
-                        tma_load_5d(smem + SM::OFF_RES + sb * 8192, &tmap_res, res_full, n_base + sb * 32, org[0], org[1],
+                        tma_load_5d(smem + OFF_RES + sb * 8192, &tmap_res, res_full, n_base + sb * 32, org[0], org[1],
                                     org[2], org[3]);
                 }
             }
@@ -159,8 +167,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * ACC_STRIDE;
                 for (int i = 0; i < total_iters; ++i, ++it) {
-                    const int s = it % TG2_STAGES;
-                    mbar_wait(&full_bar[s], (it / TG2_STAGES) & 1);
+                    const int s = it % NS;
+                    mbar_wait(&full_bar[s], (it / NS) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + SM::A_BYTES;
@@ -179,8 +187,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int swz = (r >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
-        uint8_t* out_row = smem + SM::OFF_OUT + r * 64;
-        const uint8_t* res_row = smem + SM::OFF_RES + r * 64;
+        uint8_t* out_row = smem + OFF_OUT + r * 64;
+        const uint8_t* res_row = smem + OFF_RES + r * 64;
         const bool leader = (threadIdx.x == 4 * 32);
         int local = 0;
         for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
@@ -293,7 +301,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll 1
                 for (int sb = 0; sb < n_per_tile / 32; ++sb) {
                     if (n_base + sb * 32 < p.N)
-                        tma_store_5d(&tmap_out, smem + SM::OFF_OUT + sb * 8192, n_base + sb * 32, org[0], org[1], org[2], org[3]);
+                        tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + sb * 32, org[0], org[1], org[2], org[3]);
                 }
                 tma_store_commit();
             }
