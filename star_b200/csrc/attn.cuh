@@ -32,6 +32,7 @@ struct AttnParams {
     float scale_log2;       // softmax scale * log2(e)
     __half* out;
     long long ldo;          // elements between consecutive rows of O
+    int order;              // attn4 MMA issue order: 0 = S,S,PV,PV per KV tile; 1 = S0,PV1,S1,PV0 (anti-phase)
 };
 
 struct AttnSmem {

@@ -133,21 +133,32 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // Issue order = event order of two softmax groups running half a period apart:
             //   S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)     (the ncu capture of the first attn4 showed the groups
             //   waiting ~25 % of their time for PV(j-1), queued behind both S(j+1), profiles/r01_ncu_attn4.txt)
-            for (int j = 0; j < nt; ++j) {
-                const bool more = (j + 1 < nt);
-                if (more) {
-                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
-                    next_s(0, j);
+            if (p.order == 1) {
+                for (int j = 0; j < nt; ++j) {
+                    const bool more = (j + 1 < nt);
+                    if (more) {
+                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                        next_s(0, j);
+                    }
+                    if (j > 0) {
+                        if (ntq > 1) issue_pv(1, j - 1);
+                        umma_commit(&kv_empty[(j - 1) % A4_KV_STAGES]);
+                    }
+                    if (more && ntq > 1) next_s(1, j);
+                    issue_pv(0, j);
                 }
-                if (j > 0) {
-                    if (ntq > 1) issue_pv(1, j - 1);
-                    umma_commit(&kv_empty[(j - 1) % A4_KV_STAGES]);
+                if (ntq > 1) issue_pv(1, nt - 1);
+                umma_commit(&kv_empty[(nt - 1) % A4_KV_STAGES]);
+            } else {
+                for (int j = 0; j < nt; ++j) {
+                    if (j + 1 < nt) {
+                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                        for (int t = 0; t < ntq; ++t) next_s(t, j);
+                    }
+                    for (int t = 0; t < ntq; ++t) issue_pv(t, j);
+                    umma_commit(&kv_empty[j % A4_KV_STAGES]);
                 }
-                if (more && ntq > 1) next_s(1, j);
-                issue_pv(0, j);
             }
-            if (ntq > 1) issue_pv(1, nt - 1);
-            umma_commit(&kv_empty[(nt - 1) % A4_KV_STAGES]);
         }
     } else if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");

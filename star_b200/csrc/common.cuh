@@ -183,7 +183,8 @@ STAR_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // below the fp16 rounding of the result): 2 MUFU + ~12 FMA-pipe ops instead of libdevice erff's ~30.
 STAR_DEVINL float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -193,6 +194,7 @@ STAR_DEVINL float erf_as(float x) {
     return copysignf(r, x);
 }
 STAR_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+STAR_DEVINL float gelu_erf_libm(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 STAR_DEVINL float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 STAR_DEVINL uint32_t pack_half2(float a, float b) {

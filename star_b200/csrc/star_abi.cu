@@ -17,6 +17,7 @@
 #include "attn3.cuh"
 #include "attn4.cuh"
 #include "rowops.cuh"
+#include "tattn2.cuh"
 #include "tapgemm.cuh"
 #include "tapgemm2.cuh"
 
@@ -27,7 +28,11 @@ namespace {
 thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 148;
+int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
 int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
+int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
+int g_attn_order = 0;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
+int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
 int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
 int g_attn_poly = 0;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
 std::atomic<long long> g_launches{0};
@@ -169,7 +174,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     p.K = d.K;
     p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
     p.N = d.N;
-    p.flags = d.flags;
+    p.flags = d.flags | g_gemm_flags;
     p.bias = (const __half*)d.bias;
     p.rowvec = (const __half*)d.rowvec;
     p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
@@ -215,6 +220,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     }
     const int grid = (int)std::min<long long>(total, g_num_sms);
     ex.stages = TapGemm2Smem<BN>::stages(d.residual != nullptr);
+    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
     tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
     return 0;
@@ -283,8 +289,16 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 16 * TA2_PITCH));
+    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 32 * TA2_PITCH));
+    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 48 * TA2_PITCH));
+    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 64 * TA2_PITCH));
+    if (const char* e = getenv("STAR_TATTN_IMPL")) g_tattn_impl = atoi(e);
     if (const char* e = getenv("STAR_GEMM_IMPL")) g_gemm_impl = atoi(e);
     if (const char* e = getenv("STAR_ATTN_IMPL")) g_attn_impl = atoi(e);
+    if (const char* e = getenv("STAR_ATTN_ORDER")) g_attn_order = atoi(e);
+    if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
+    if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
     if (const char* e = getenv("STAR_ATTN_POLY")) g_attn_poly = atoi(e);
     STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TA_WARPS * 2 * TA_MAXT * 128));
@@ -436,6 +450,7 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
+    p.order = g_attn_order;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
     const bool multi = Nk > AT_BKV && Nq > AT_BQ;
     if (g_attn_impl == 4 || (g_attn_impl == 0 && multi)) {
@@ -481,13 +496,30 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
 
 int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,
                             int heads, int Ci, float scale, void* stream) {
-    if (T > TA_MAXT) return fail("star_temporal_attention: T=%d exceeds %d", T, TA_MAXT);
+    if (T > TA_MAXT || T < 1) return fail("star_temporal_attention: T=%d outside [1, %d]", T, TA_MAXT);
     if (ld % 8 || ldo % 8 || Ci % 8) return fail("star_temporal_attention: ld/ldo/Ci must be multiples of 8");
+    if ((reinterpret_cast<uintptr_t>(QKV) | reinterpret_cast<uintptr_t>(O)) % 16) return fail("star_temporal_attention: pointers must be 16-byte aligned");
     const long long items = (long long)B * HW * heads;
-    const long long blocks = (items + TA_WARPS - 1) / TA_WARPS;
-    temporal_attn_kernel<<<(unsigned)blocks, TA_WARPS * 32, TA_WARPS * 2 * T * 128, (cudaStream_t)stream>>>(
-        (const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale);
-    STAR_LAUNCH_CHECK("temporal_attn");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_tattn_impl == 1) {
+        const long long blocks = (items + TA_WARPS - 1) / TA_WARPS;
+        temporal_attn_kernel<<<(unsigned)blocks, TA_WARPS * 32, TA_WARPS * 2 * T * 128, st>>>(
+            (const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale);
+        STAR_LAUNCH_CHECK("temporal_attn");
+        return 0;
+    }
+    const int tp = (T + 15) / 16 * 16;
+    const unsigned grid = (unsigned)std::min<long long>((items + TA2_WARPS - 1) / TA2_WARPS, (long long)g_num_sms * 2);
+    const size_t smem = (size_t)TA2_WARPS * 3 * tp * TA2_PITCH;
+#define STAR_TA2(TPV) temporal_attn2_kernel<TPV><<<grid, TA2_WARPS * 32, smem, st>>>((const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale)
+    switch (tp) {
+        case 16: STAR_TA2(16); break;
+        case 32: STAR_TA2(32); break;
+        case 48: STAR_TA2(48); break;
+        default: STAR_TA2(64); break;
+    }
+#undef STAR_TA2
+    STAR_LAUNCH_CHECK("temporal_attn2");
     return 0;
 }
 

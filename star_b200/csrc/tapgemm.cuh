@@ -29,6 +29,7 @@ constexpr int TG_THREADS = 192;
 enum TapGemmFlags : int {
     TG_GEGLU = 1,        // W has 2N rows (value | gate); out = value * gelu_erf(gate)
     TG_SILU_OUT = 2,     // out = silu(acc)
+    TG_GELU_LIBM = 4,    // debug: libdevice erff instead of erf_as in the GEGLU epilogue
 };
 
 struct TapGemmParams {

@@ -241,7 +241,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int e = 0; e < 8; ++e) {
                             float xv = __uint_as_float(v[u * 8 + e]), gv = __uint_as_float(g[u * 8 + e]);
                             if (inb) { xv += bv[e]; gv += bg[e]; }
-                            f[u * 8 + e] = xv * gelu_erf_f(gv);
+                            f[u * 8 + e] = xv * ((p.flags & TG_GELU_LIBM) ? gelu_erf_libm(gv) : gelu_erf_f(gv));
                         }
                     }
                 } else {

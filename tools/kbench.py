@@ -114,8 +114,19 @@ def bench_rowops():
     report("concat_add 320|320", timeit(lambda: O.concat_add(a, bb, bb)), bytes_=5.0 * R * 320 * 2)
 
 
+def clocks():
+    import subprocess
+    try:
+        o = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_event_reasons.active",
+                            "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout.strip()
+        print(f"# nvidia-smi (idle, after group): {o}", flush=True)
+    except Exception as e:
+        print("# nvidia-smi failed", e)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attention", "linear", "conv", "rowops"]
     print(f"# peaks used: {PEAK}")
     for w in which:
         globals()["bench_" + w]()
+        clocks()
