@@ -48,17 +48,24 @@ STAR_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug (lost arrive / wrong parity) traps instead of hanging the GPU.
-#ifndef STAR_WAIT_LIMIT
-#define STAR_WAIT_LIMIT (1u << 24)
+// Bounded wait: a protocol bug (lost arrive / wrong parity) traps after ~2 s of SM clocks instead of hanging
+// the GPU (try_wait itself may block for a system-dependent time, so the bound is on clock64, not on spins).
+#ifndef STAR_WAIT_CYCLES
+#define STAR_WAIT_CYCLES 4000000000ll
 #endif
 STAR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > STAR_WAIT_LIMIT) {
-            printf("star: mbarrier wait timed out (block %d,%d,%d thread %d bar smem+0x%x parity %u)\n", blockIdx.x,
-                   blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-            __trap();
+        if ((++spins & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > STAR_WAIT_CYCLES) {
+                printf("star: mbarrier wait timed out (block %d,%d,%d thread %d bar smem+0x%x parity %u)\n", blockIdx.x,
+                       blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+                __trap();
+            }
         }
     }
 }

@@ -245,8 +245,10 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
 // gate_mode 2: y = LN(x * sigmoid(w0*max_c(x) + w1*mean_c(x)))   temporal LIEM (unet_v2v.py:402-411, :481-487)
 // One warp per row; the row lives in registers (C <= 1280 -> <= 5 x 8 values per lane).
 constexpr int LN_MAX_OCT = 5;
+// Persistent warps (grid-stride over rows) with the NEXT row of the warp prefetched as packed 16-byte registers;
+// register use is kept low (launch bounds) so that ~50 warps/SM x 2 rows are in flight (HBM latency hiding).
 template <int LN_OCT>          // 16-byte column groups per lane: 2 (C <= 512), 3 (C <= 768), 5 (C <= 1280)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LN_OCT <= 2 ? 5 : (LN_OCT == 3 ? 4 : 2))
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                  __half* __restrict__ out, long long rows, int C, float eps, int gate_mode,
                  const __half* __restrict__ gate, float w0, float w1) {
@@ -255,35 +257,31 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
     long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int O = C / 8;
-    // affine parameters stay in registers for all rows of this warp
-    uint4 gm_u[LN_OCT], bt_u[LN_OCT], cur[LN_OCT], nxt[LN_OCT];
+    const float inv_c = 1.0f / (float)C;
+    uint4 nxt[LN_OCT];
 #pragma unroll
     for (int i = 0; i < LN_OCT; ++i) {
         const int oc = lane + 32 * i;
-        if (oc < O) {
-            gm_u[i] = __ldg(reinterpret_cast<const uint4*>(gamma + oc * 8));
-            bt_u[i] = __ldg(reinterpret_cast<const uint4*>(beta + oc * 8));
-            cur[i] = __ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8));
-        }
+        if (oc < O) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8));
     }
     for (; row < rows; row += nwarps) {
-        const long long nrow = row + nwarps;
-        if (nrow < rows) {                              // prefetch the next row of this warp
-#pragma unroll
-            for (int i = 0; i < LN_OCT; ++i) {
-                const int oc = lane + 32 * i;
-                if (oc < O) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + nrow * C + oc * 8));
-            }
-        }
         float v[LN_OCT][8];
         float s = 0.f, mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < LN_OCT; ++i) {
             const int oc = lane + 32 * i;
             if (oc < O) {
-                unpack8(cur[i], v[i]);
+                unpack8(nxt[i], v[i]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { s += v[i][j]; mx = fmaxf(mx, v[i][j]); }
+            }
+        }
+        const long long nrow = row + nwarps;
+        if (nrow < rows) {                              // prefetch the next row of this warp
+#pragma unroll
+            for (int i = 0; i < LN_OCT; ++i) {
+                const int oc = lane + 32 * i;
+                if (oc < O) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + nrow * C + oc * 8));
             }
         }
         if (gate_mode != 0) {
@@ -294,7 +292,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                 s = warp_sum(s);
                 mx = warp_max(mx);
                 // reference computes max / mean / Linear(2->1) / sigmoid in fp16 (autocast keeps input dtype)
-                const float mean_h = __half2float(__float2half_rn(s / (float)C));
+                const float mean_h = __half2float(__float2half_rn(s * inv_c));
                 const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
                 g = __half2float(__float2half_rn(sigmoid_f(lin)));
             }
@@ -311,7 +309,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                 }
             }
         }
-        const float mean = warp_sum(s) / (float)C;
+        const float mean = warp_sum(s) * inv_c;
         float var = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_OCT; ++i) {
@@ -321,18 +319,17 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                 for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var = fmaf(d, d, var); }
             }
         }
-        const float rstd = rsqrtf(warp_sum(var) / (float)C + eps);
+        const float rstd = rsqrtf(warp_sum(var) * inv_c + eps);
 #pragma unroll
         for (int i = 0; i < LN_OCT; ++i) {
             const int oc = lane + 32 * i;
             if (oc < O) {
-                float gm[8], bt[8], y[8];
-                unpack8(gm_u[i], gm);
-                unpack8(bt_u[i], bt);
+                float gm[8], bt[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + oc * 8)), gm);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(beta + oc * 8)), bt);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
-                *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(y);
-                cur[i] = nxt[i];
+                for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+                *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(v[i]);
             }
         }
     }

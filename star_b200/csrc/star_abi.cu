@@ -555,7 +555,7 @@ int star_layernorm(const void* X, const void* gamma, const void* beta, void* out
     if (C % 8 || C / 8 > 32 * LN_MAX_OCT) return fail("star_layernorm: unsupported C=%d", C);
     const int wpb = 8;
     const long long want = (rows + wpb - 1) / wpb;
-    const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 16);
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 6);
     const int oct = (C / 8 + 31) / 32;
 #define STAR_LN_LAUNCH(N)                                                                                          \
     layernorm_kernel<N><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma,          \

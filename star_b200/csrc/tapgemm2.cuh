@@ -118,16 +118,16 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             const uint32_t tx = (uint32_t)p.box_rows * 128u + (uint32_t)SM::B_BYTES;
-            int it = 0, local = 0;
+            int s = 0, local = 0;
+            uint32_t ph = 0;                              // ring phase (no runtime div/mod in the issue loops)
             for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
                 int org[4], n_tile;
                 tile_origin(tile, org, n_tile);
                 for (int t = 0; t < p.ntaps; ++t) {
                     const int c1 = org[0] + p.tap[t][0], c2 = org[1] + p.tap[t][1];
                     const int c3 = org[2] + p.tap[t][2], c4 = org[3] + p.tap[t][3];
-                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                        const int s = it % NS;
-                        mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
                         uint8_t* sa = smem + s * SM::STAGE_BYTES;
                         uint8_t* sb = sa + SM::A_BYTES;
                         mbar_expect_tx(&full_bar[s], tx);
@@ -139,6 +139,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * (BN / 2));
                             tma_load_2d(sb + (BN / 2) * 128, &tmap_w, &full_bar[s], kw, p.N + n_tile * (BN / 2));
                         }
+                        if (++s == NS) { s = 0; ph ^= 1; }
                     }
                 }
                 if (has_res) {
@@ -160,15 +161,15 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(TG_BM, BN, 0, 0);
-            int it = 0, local = 0;
+            int s = 0, local = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
                 const int buf = local & 1;
                 mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * ACC_STRIDE;
-                for (int i = 0; i < total_iters; ++i, ++it) {
-                    const int s = it % NS;
-                    mbar_wait(&full_bar[s], (it / NS) & 1);
+                for (int i = 0; i < total_iters; ++i) {
+                    mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + SM::A_BYTES;
@@ -177,6 +178,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         umma_f16_ss(acc, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
                                     idesc, (i > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty_bar[s]);
+                    if (++s == NS) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);
             }
