@@ -231,7 +231,10 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     const bool aligned = (d.N % 32 == 0) && (d.ldo % 8 == 0) && (reinterpret_cast<uintptr_t>(d.out) % 16 == 0) &&
                          (!d.residual || ((d.ldres % 8 == 0) && (reinterpret_cast<uintptr_t>(d.residual) % 16 == 0))) &&
                          (!geglu || d.N % 64 == 0);
-    if (aligned && g_gemm_impl != 1) {
+    // Non-persistent kernel (2 CTAs/SM, two interleaved MMA streams) is measurably faster for the long-reduction,
+    // wide-N convolutions (profiles/r01_kbench_ab_experiments.txt); the persistent one wins everywhere else.
+    const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu;
+    if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
         if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm2_bn<160>(d, st);
         return launch_tapgemm2_bn<128>(d, st);
     }
@@ -286,6 +289,7 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
@@ -459,6 +463,7 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
         switch (g_attn_poly) {
             case 4: attn4_fwd_kernel<4><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
             case 3: attn4_fwd_kernel<3><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 16: attn4_fwd_kernel<16><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
             default: attn4_fwd_kernel<0><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
         }
         STAR_LAUNCH_CHECK("attn4_fwd");

@@ -5,15 +5,16 @@
 //   * the epilogue is fully coalesced: residual tile arrives by TMA (prefetched during the main loop),
 //     results are staged in swizzled shared memory and leave through TMA stores (hardware clips ragged
 //     tile edges and the N tail), bias / time-embedding rows are read with 128-bit loads
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
-// warps 4-7 epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
+// warps 4-11 epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and every other 32-column chunk
+// (the GEGLU / residual epilogues are instruction-bound with one warp per quadrant).
 #pragma once
 #include "common.cuh"
 #include "tapgemm.cuh"
 
 namespace star {
 
-constexpr int TG2_THREADS = 256;
+constexpr int TG2_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle; warps 4-11: epilogue (two warps per TMEM lane quadrant)
 constexpr int TG2_MAX_STAGES = 6;
 
 template <int BN>
@@ -39,7 +40,7 @@ STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int
 STAR_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct TapGemm2Extra {
     int num_tiles;        // m_tiles * n_tiles
@@ -90,10 +91,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&acc_full[b], 1);
-                mbar_init(&acc_empty[b], 128);
+                mbar_init(&acc_empty[b], 256);
             }
             mbar_init(res_full, 1);
-            mbar_init(res_empty, 128);
+            mbar_init(res_empty, 256);
             fence_barrier_init();
         }
         __syncwarp();
@@ -184,8 +185,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------ epilogue warps 4..7
+        // ------------------------------------------------ epilogue warps 4..11
         const int q = warp & 3;
+        const int ehalf = (warp - 4) >> 2;                  // this warp handles 32-column chunks with (chunk & 1) == ehalf
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int swz = (r >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
@@ -221,8 +223,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (leader) tma_store_wait_read();
             epi_bar_sync();
             const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
+            const int last_c0 = ((n_per_tile / 32 - 1 - ehalf) & ~1) * 32 + ehalf * 32;   // last chunk of this warp
 #pragma unroll 1
-            for (int c0 = 0; c0 < n_per_tile; c0 += 32) {
+            for (int c0 = ehalf * 32; c0 < n_per_tile; c0 += 64) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(t_row + c0, v);
@@ -243,7 +246,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int e = 0; e < 8; ++e) {
                             float xv = __uint_as_float(v[u * 8 + e]), gv = __uint_as_float(g[u * 8 + e]);
                             if (inb) { xv += bv[e]; gv += bg[e]; }
-                            f[u * 8 + e] = xv * ((p.flags & TG_GELU_LIBM) ? gelu_erf_libm(gv) : gelu_erf_f(gv));
+                            f[u * 8 + e] = xv * gelu_erf_f(gv);
                         }
                     }
                 } else {
@@ -257,7 +260,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int e = 0; e < 8; ++e) f[u * 8 + e] = __uint_as_float(v[u * 8 + e]) + (inb ? bv[e] : 0.f);
                     }
                 }
-                if (c0 + 32 >= n_per_tile) {                 // last TMEM read of this accumulator: hand it back
+                if (c0 == last_c0) {                         // last TMEM read of this warp for this accumulator
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }
