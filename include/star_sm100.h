@@ -52,9 +52,11 @@ int star_conv2d_3x3_s2(const void* X, const void* W9, const void* bias, void* ou
  * (unet_v2v.py:1209-1220). */
 int star_conv_t3(const void* X, const void* W3, const void* bias, const void* residual, long long ldres, void* out,
                  long long ldo, int B, int T, long long HW, int Cin, int Cout, void* stream);
-/* Stem convs with Cin = 4 (unet_v2v.py:1353 input conv, :2128 input_hint_block); W9 as above. */
-int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, int BT,
-                       int H, int W, int Cout, void* stream);
+/* Stem convs with Cin = 4 (unet_v2v.py:1353 input conv, :2128 input_hint_block); W9 as above.  Runs as im2col
+ * (K = 36 padded to 64) + tensor-core GEMM; ws = scratch of star_conv2d_c4_workspace_bytes(). */
+long long star_conv2d_c4_workspace_bytes(int BT, int H, int W, int Cout);
+int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, void* ws,
+                       int BT, int H, int W, int Cout, void* stream);
 
 /* softmax(Q K^T * scale) V, head_dim 64, heads side by side along the row (column offset h*64); batch b uses rows
  * [b*Nq,(b+1)*Nq) of Q/O and rows [(b/kv_batch_div)*Nk, ...) of K/V.  Replaces

@@ -65,7 +65,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_init(q_full, 1);
             for (int s = 0; s < A4_KV_STAGES; ++s) {
                 mbar_init(&kv_full[s], 1);
-                mbar_init(&kv_empty[s], 1);
+                mbar_init(&kv_empty[s], (p.order == 2 && ntq > 1) ? 2 : 1);
             }
             for (int t = 0; t < 2; ++t) {
                 mbar_init(&s_full[t], 1);
@@ -114,7 +114,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
-            for (int t = 0; t < ntq; ++t) issue_s(t, 0);
+            for (int t = 0; t < ((p.order == 2) ? 1 : ntq); ++t) issue_s(t, 0);
             auto issue_pv = [&](int t, int j) {
                 mbar_wait(&p_full[t], j & 1);
                 tc_fence_after();
@@ -133,7 +133,17 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // Issue order = event order of two softmax groups running half a period apart:
             //   S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)     (the ncu capture of the first attn4 showed the groups
             //   waiting ~25 % of their time for PV(j-1), queued behind both S(j+1), profiles/r01_ncu_attn4.txt)
-            if (p.order == 1) {
+            if (p.order == 2) {
+                // independent pipeline per query tile: this thread only drives tile 0 (warp 2 drives tile 1)
+                for (int j = 0; j < nt; ++j) {
+                    if (j + 1 < nt) {
+                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                        next_s(0, j);
+                    }
+                    issue_pv(0, j);
+                    umma_commit(&kv_empty[j % A4_KV_STAGES]);
+                }
+            } else             if (p.order == 1) {
                 for (int j = 0; j < nt; ++j) {
                     const bool more = (j + 1 < nt);
                     if (more) {
@@ -162,6 +172,41 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
     } else if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 2 && lane == 0 && p.order == 2 && ntq > 1) {
+            // second MMA-issuing thread: query tile 1
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);
+            const uint32_t q_addr = smem_u32(smem + Attn4Smem::OFF_Q + Attn4Smem::TILE);
+            auto issue_s1 = [&](int j) {
+                const uint32_t k_addr = smem_u32(smem + Attn4Smem::OFF_K + (j % A4_KV_STAGES) * Attn4Smem::TILE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base + 128, umma_desc_sw128(q_addr + k * 32, 16, 1024),
+                                umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[1]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s1(0);
+            for (int j = 0; j < nt; ++j) {
+                if (j + 1 < nt) {
+                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                    mbar_wait(&s_free[1], j & 1);
+                    tc_fence_after();
+                    issue_s1(j + 1);
+                }
+                mbar_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + (j % A4_KV_STAGES) * Attn4Smem::TILE);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_f16_ts(tmem_base + 256 + 64, tmem_base + 384 + 64 + k * 8,
+                                umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&pv_done[1]);
+                umma_commit(&kv_empty[j % A4_KV_STAGES]);
+            }
+        }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int t = (warp - 4) >> 2;                   // query tile of this warpgroup
@@ -195,8 +240,17 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     for (int i = 0; i < 128; ++i)
                         if (kbase + i >= p.Nk) v[i] = 0xff800000u;      // -inf
                 }
+                {
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
 #pragma unroll
-                for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                    for (int i = 0; i < 128; i += 8) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+                    }
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                }
                 const float mc = mx * sl2;
                 float factor = 1.f;
                 bool need = false;

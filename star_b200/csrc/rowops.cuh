@@ -63,56 +63,36 @@ __global__ void tokens_to_nchw5_kernel(const __half* __restrict__ x, long long l
 }
 
 // ------------------------------------------------------------------ stem conv: 3x3, Cin = 4 (unet_v2v.py:1353, :2128)
-// X [BT, H, W, 4] fp16; Wt [Cout][9*4] (tap-major, then cin); out [BT*H*W, Cout] (+bias, +residual)
-__global__ void conv3x3_c4_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
-                                  const __half* __restrict__ bias, const __half* __restrict__ residual,
-                                  __half* __restrict__ out, int BT, int H, int W, int Cout) {
-    extern __shared__ __half w_s[];      // [36][Cout]
-    const int groups = Cout / 8;
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 36 * Cout; i += blockDim.x * blockDim.y) {
-        const int k = i / Cout, n = i % Cout;
-        w_s[i] = wt[n * 36 + k];
-    }
-    __syncthreads();
+// stem conv as a tensor-core GEMM: im2col of the 4-channel input to K = 64 (36 taps*channels, zero padded) and the
+// matching zero-padded weight matrix [Cout, 64]; the product runs on the tap-GEMM kernel.
+__global__ void im2col_c4_kernel(const __half* __restrict__ x, __half* __restrict__ col, int BT, int H, int W) {
     const long long npix = (long long)BT * H * W;
-    const long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    if (pix >= npix || threadIdx.x >= groups) return;
-    const int w0 = (int)(pix % W);
-    const int h0 = (int)((pix / W) % H);
-    const long long bt = pix / ((long long)W * H);
-    float acc[8];
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+        const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H);
+        const long long bt = pix / ((long long)W * H);
+        uint2 v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? __half2float(bias[threadIdx.x * 8 + j]) : 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = make_uint2(0, 0);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int hh = h0 + r - 1;
-        if (hh < 0 || hh >= H) continue;
+        for (int r = 0; r < 3; ++r) {
+            const int hh = h0 + r - 1;
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int ww = w0 + s - 1;
-            if (ww < 0 || ww >= W) continue;
-            const uint2 xv = *reinterpret_cast<const uint2*>(x + ((bt * H + hh) * W + ww) * 4);
-            const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-            const float2 x01 = __half22float2(xh[0]), x23 = __half22float2(xh[1]);
-            const float xi[4] = {x01.x, x01.y, x23.x, x23.y};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 wv = *reinterpret_cast<const uint4*>(w_s + ((r * 3 + s) * 4 + c) * Cout + threadIdx.x * 8);
-                float wf[8];
-                unpack8(wv, wf);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xi[c], wf[j], acc[j]);
+            for (int s2 = 0; s2 < 3; ++s2) {
+                const int ww = w0 + s2 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    v[r * 3 + s2] = __ldg(reinterpret_cast<const uint2*>(x + ((bt * H + hh) * W + ww) * 4));
             }
         }
-    }
-    if (residual) {
-        float rf[8];
-        unpack8(*reinterpret_cast<const uint4*>(residual + pix * Cout + threadIdx.x * 8), rf);
-        // reference adds the hint feature to the fp16 conv output (unet_v2v.py:2193): round first
+        uint4* dst = reinterpret_cast<uint4*>(col + pix * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = __half2float(__float2half_rn(acc[j])) + rf[j];
+        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
     }
-    *reinterpret_cast<uint4*>(out + pix * Cout + threadIdx.x * 8) = pack8(acc);
+}
+__global__ void pad_w36_kernel(const __half* __restrict__ w9, __half* __restrict__ w64, int Cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * 64) return;
+    const int n = i / 64, k = i % 64;
+    w64[i] = k < 36 ? w9[n * 36 + k] : __float2half_rn(0.f);
 }
 
 // ------------------------------------------------------------------ GroupNorm (32 groups)

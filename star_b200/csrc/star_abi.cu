@@ -416,17 +416,23 @@ int star_conv_t3(const void* X, const void* W3, const void* bias, const void* re
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
 
-int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, int BT,
-                       int H, int W, int Cout, void* stream) {
-    if (Cout % 8 || Cout / 8 > 64) return fail("star_conv2d_3x3_c4: Cout must be a multiple of 8, <= 512");
-    const int gx = Cout / 8;
-    dim3 block(gx, std::max(1, 256 / gx));
-    const long long npix = (long long)BT * H * W;
-    const long long blocks = (npix + block.y - 1) / block.y;
-    conv3x3_c4_kernel<<<(unsigned)blocks, block, 36 * Cout * sizeof(__half), (cudaStream_t)stream>>>(
-        (const __half*)X, (const __half*)W9, (const __half*)bias, (const __half*)residual, (__half*)out, BT, H, W, Cout);
-    STAR_LAUNCH_CHECK("conv3x3_c4");
-    return 0;
+long long star_conv2d_c4_workspace_bytes(int BT, int H, int W, int Cout) {
+    return ((long long)BT * H * W * 64 + (long long)Cout * 64) * 2;
+}
+
+int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const void* residual, void* out, void* ws,
+                       int BT, int H, int W, int Cout, void* stream) {
+    STAR_CHECK_INIT();
+    if (Cout % 8) return fail("star_conv2d_3x3_c4: Cout must be a multiple of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)BT * H * W;
+    __half* col = (__half*)ws;
+    __half* w64 = col + rows * 64;
+    pad_w36_kernel<<<(Cout * 64 + 255) / 256, 256, 0, st>>>((const __half*)W9, w64, Cout);
+    STAR_LAUNCH_CHECK("pad_w36");
+    im2col_c4_kernel<<<grid_for(rows, 256), 256, 0, st>>>((const __half*)X, col, BT, H, W);
+    STAR_LAUNCH_CHECK("im2col_c4");
+    return star_linear(col, 64, w64, bias, nullptr, 1, residual, Cout, out, Cout, rows, 64, Cout, 0, stream);
 }
 
 int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,

@@ -164,7 +164,8 @@ def conv2d_3x3_c4(x, w9, bias=None, residual=None):
     Cout = w9.shape[0]
     out = torch.empty((BT * H * W, Cout), dtype=HALF, device=x.device)
     L = _L.get_lib()
-    _L.check(L.star_conv2d_3x3_c4(_p(x), _p(w9), _p(bias), _p(residual), _p(out), BT, H, W, Cout, _st()),
+    ws = torch.empty(L.star_conv2d_c4_workspace_bytes(BT, H, W, Cout), dtype=torch.uint8, device=x.device)
+    _L.check(L.star_conv2d_3x3_c4(_p(x), _p(w9), _p(bias), _p(residual), _p(out), _p(ws), BT, H, W, Cout, _st()),
              "star_conv2d_3x3_c4")
     return out
 
