@@ -31,10 +31,10 @@ int g_num_sms = 148;
 int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
 int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
 int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
-int g_attn_order = 0;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
+int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
 int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
 int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
-int g_attn_poly = 0;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
+int g_attn_poly = 4;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
 std::atomic<long long> g_launches{0};
 
 int fail(const char* fmt, ...) {
