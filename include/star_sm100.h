@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define STAR_FLAG_GEGLU 1     /* W has 2N rows (value|gate): out = value * gelu_erf(gate)  (unet_v2v.py:496-504) */
+#define STAR_FLAG_GELU_TANH 8 /* out = gelu_tanh(acc) (sat MLP activation, cogvideox-based/transformer.py:202-312)  */
 #define STAR_FLAG_SILU_OUT 2  /* out = silu(acc)                                            (unet_v2v.py:1340-1342) */
 
 int star_version(void);
@@ -37,6 +38,13 @@ int star_init(int device);
 int star_linear(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
                 long long rowvec_div, const void* residual, long long ldres, void* out, long long ldo,
                 long long rows, int K, int N, int flags, void* stream);
+
+/* star_linear with a per-output-column scale applied before the residual add:
+ * out = residual + colscale[n] * (acc + bias[n])  -- the adaLN gates of the CogVideoX DiT layer
+ * (cogvideox-based/sat/dit_video_concat.py:543-544,:560-561).  flags may also carry STAR_FLAG_GELU_TANH. */
+int star_linear_ex(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
+                   long long rowvec_div, const void* colscale, const void* residual, long long ldres, void* out,
+                   long long ldo, long long rows, int K, int N, int flags, void* stream);
 
 /* Conv2d 3x3 stride 1 pad 1 on X[BT,H,W,Cin]; W9 = weight permuted to [Cout][3][3][Cin]; rowvec = per-clip time
  * embedding added before the next GroupNorm; replaces cuDNN at unet_v2v.py:612,:639,:553-554,:1552. */
@@ -81,6 +89,18 @@ int star_layernorm(const void* X, const void* gamma, const void* beta, void* out
  * flattened [2][7][7]; mm_ws = scratch rows*2 fp16; gate = rows fp16. */
 int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* gate, int BT, int H, int W, int C,
                            void* stream);
+
+/* CogVideoX DiT layer helpers (cogvideox-based/sat/dit_video_concat.py).
+ * star_row_gate: out = X * g(row); mode 1: g = gate[row] (spatial LIEM, :523-527, gate from star_liem_spatial_gate);
+ * mode 2: g = sigmoid(w0*max_c + w1*mean_c) (temporal LIEM, :529-531).
+ * star_qk_ln_rope: in-place per-head LayerNorm(64) of q (column 0) and k (column koff) of QKV[rows, ld] (:583-587)
+ * followed by the 3-D rotary embedding of the image tokens (rows with (row % seq) >= text_len; :306-333);
+ * cos/sin are fp32 [seq - text_len, 64]. */
+int star_row_gate(const void* X, void* out, long long rows, int C, int mode, const void* gate, float w0, float w1,
+                  void* stream);
+int star_qk_ln_rope(void* QKV, long long ld, long long rows, int heads, int koff, const void* qg, const void* qb,
+                    const void* kg, const void* kb, const void* cos_f32, const void* sin_f32, int seq, int text_len,
+                    float eps, void* stream);
 
 /* out[rows, Ca+Cb] = [a | b (+c)]  (torch.cat + control residual, unet_v2v.py:1792); c may be NULL */
 int star_concat_add(const void* a, int Ca, const void* b, const void* c, int Cb, void* out, long long rows,

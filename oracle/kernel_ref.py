@@ -182,3 +182,54 @@ def sinusoidal(t, dim):
 
 def silu(x):
     return F.silu(_f(x)).to(HALF)
+
+
+FLAG_GELU_TANH = 8
+
+
+def linear_ex(a, w, bias=None, colscale=None, residual=None, flags=0, out=None):
+    acc = _f(a) @ _f(w).t()
+    if bias is not None:
+        acc = acc + _f(bias)
+    if flags & FLAG_GELU_TANH:
+        acc = F.gelu(acc, approximate="tanh")
+    if colscale is not None:
+        acc = acc * _f(colscale)
+    if residual is not None:
+        acc = acc + _f(residual)
+    res = acc.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def row_gate(x, mode, gate=None, w0=0.0, w1=0.0, out=None):
+    xf = _f(x)
+    if mode == 1:
+        g = _f(gate)[:, None]
+    else:
+        mx = xf.max(dim=-1, keepdim=True)[0]
+        mean = xf.mean(dim=-1, keepdim=True).to(HALF).float()
+        g = torch.sigmoid((w0 * mx + w1 * mean).to(HALF).float()).to(HALF).float()
+    res = (xf * g).to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def qk_ln_rope(qkv, heads, koff, qg, qb, kg, kb, cos, sin, seq, text_len, eps=1e-6):
+    rows = qkv.shape[0]
+    tok = torch.arange(rows, device=qkv.device) % seq
+    img = tok >= text_len
+    idx = (tok - text_len).clamp(min=0)
+    c, s = cos.to(qkv.device)[idx][:, None, :], sin.to(qkv.device)[idx][:, None, :]
+    for off, g, b in ((0, qg, qb), (koff, kg, kb)):
+        x = _f(qkv[:, off:off + heads * 64]).reshape(rows, heads, 64)
+        x = F.layer_norm(x, (64,), _f(g), _f(b), eps).to(HALF).float()
+        xr = x.reshape(rows, heads, 32, 2)
+        rot = torch.stack((-xr[..., 1], xr[..., 0]), dim=-1).reshape(rows, heads, 64)
+        y = torch.where(img[:, None, None], x * c + rot * s, x)
+        qkv[:, off:off + heads * 64] = y.reshape(rows, heads * 64).to(HALF)
+    return qkv

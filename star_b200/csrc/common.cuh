@@ -201,7 +201,12 @@ STAR_DEVINL float erf_as(float x) {
     return copysignf(r, x);
 }
 STAR_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
-STAR_DEVINL float gelu_erf_libm(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+STAR_DEVINL float gelu_tanh_f(float x) {
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    return 0.5f * x * (1.0f + t);
+}
 STAR_DEVINL float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 STAR_DEVINL uint32_t pack_half2(float a, float b) {

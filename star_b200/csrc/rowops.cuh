@@ -228,7 +228,7 @@ constexpr int LN_MAX_OCT = 5;
 // Persistent warps (grid-stride over rows) with the NEXT row of the warp prefetched as packed 16-byte registers;
 // register use is kept low (launch bounds) so that ~50 warps/SM x 2 rows are in flight (HBM latency hiding).
 template <int LN_OCT>          // 16-byte column groups per lane: 2 (C <= 512), 3 (C <= 768), 5 (C <= 1280)
-__global__ void __launch_bounds__(256, LN_OCT <= 2 ? 5 : (LN_OCT == 3 ? 4 : 2))
+__global__ void __launch_bounds__(256, LN_OCT <= 2 ? 5 : (LN_OCT == 3 ? 4 : (LN_OCT <= 5 ? 2 : 1)))
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                  __half* __restrict__ out, long long rows, int C, float eps, int gate_mode,
                  const __half* __restrict__ gate, float w0, float w1) {
@@ -363,6 +363,94 @@ __global__ void liem_conv7_kernel(const __half* __restrict__ mm, const __half* _
     }
     const float a = __half2float(__float2half_rn(acc));      // fp16 conv output in the reference
     gate[i] = __float2half_rn(sigmoid_f(a));
+}
+
+// ------------------------------------------------------------------ CogVideoX DiT helpers (cogvideox-based/sat/dit_video_concat.py)
+// out = x * g(row): mode 1 external per-row gate (spatial LIEM, :523-527); mode 2 temporal LIEM gate
+// sigmoid(w0*max_c + w1*mean_c) computed in-kernel (:529-531).  Any C that is a multiple of 8.
+__global__ void __launch_bounds__(256)
+row_gate_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long rows, int C, int mode,
+                const __half* __restrict__ gate, float w0, float w1) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int O = C / 8;
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+        float g;
+        if (mode == 1) {
+            g = __half2float(gate[row]);
+        } else {
+            float s = 0.f, mx = -INFINITY;
+            for (int oc = lane; oc < O; oc += 32) {
+                float f[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s += f[j]; mx = fmaxf(mx, f[j]); }
+            }
+            s = warp_sum(s);
+            mx = warp_max(mx);
+            const float mean_h = __half2float(__float2half_rn(s / (float)C));
+            const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
+            g = __half2float(__float2half_rn(sigmoid_f(lin)));
+        }
+        for (int oc = lane; oc < O; oc += 32) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + oc * 8)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= g;
+            *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(f);
+        }
+    }
+}
+
+// In-place per-head LayerNorm(64) of q and k (:583-587) followed by the 3-D rotary embedding of the image tokens
+// (:306-333; interleaved pairs (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin)).  qkv [rows, ld]; q at column 0,
+// k at column `koff`; 8 lanes per (row, head, q|k), 8 elements per lane.  cos/sin: fp32 [n_img, 64].
+__global__ void __launch_bounds__(256)
+qk_ln_rope_kernel(__half* __restrict__ qkv, long long ld, long long rows, int heads, int koff,
+                  const __half* __restrict__ qg, const __half* __restrict__ qb, const __half* __restrict__ kg,
+                  const __half* __restrict__ kb, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                  int seq, int text_len, float eps) {
+    const long long ngroups = rows * heads * 2;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    if (gid >= ngroups) return;
+    const int which = (int)(gid & 1);                     // 0 = q, 1 = k
+    const int head = (int)((gid >> 1) % heads);
+    const long long row = (gid >> 1) / heads;
+    __half* ptr = qkv + row * ld + (which ? koff : 0) + head * 64 + sub * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(ptr), f);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mean = s * (1.f / 64.f);
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; var = fmaf(d, d, var); }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    var += __shfl_xor_sync(0xffffffffu, var, 2);
+    var += __shfl_xor_sync(0xffffffffu, var, 4);
+    const float rstd = rsqrtf(var * (1.f / 64.f) + eps);
+    float gm[8], bt[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>((which ? kg : qg) + sub * 8)), gm);
+    unpack8(__ldg(reinterpret_cast<const uint4*>((which ? kb : qb) + sub * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __half2float(__float2half_rn((f[j] - mean) * rstd * gm[j] + bt[j]));   // LN output is fp16/bf16 in the reference
+    const int tok = (int)(row % seq);
+    if (tok >= text_len) {
+        const float* c = cos_t + (long long)(tok - text_len) * 64 + sub * 8;
+        const float* sn = sin_t + (long long)(tok - text_len) * 64 + sub * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const float x1 = f[j], x2 = f[j + 1];
+            f[j] = x1 * c[j] - x2 * sn[j];
+            f[j + 1] = x2 * c[j + 1] + x1 * sn[j + 1];
+        }
+    }
+    *reinterpret_cast<uint4*>(ptr) = pack8(f);
 }
 
 // ------------------------------------------------------------------ temporal self-attention (unet_v2v.py:483-489)

@@ -100,7 +100,7 @@ struct TapDesc {
     int ntaps;
     int tap[TG_MAX_TAPS][4];
     int K, N, flags;
-    const void *W, *bias, *rowvec, *residual;
+    const void *W, *bias, *rowvec, *residual, *colscale;
     long long rowvec_div, ldres, ldo;
     void* out;
 };
@@ -179,6 +179,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     p.rowvec = (const __half*)d.rowvec;
     p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
     p.residual = (const __half*)d.residual;
+    p.colscale = (const __half*)d.colscale;
     p.res_ld = d.ldres;
     p.out = (__half*)d.out;
     p.out_ld = d.ldo;
@@ -233,7 +234,9 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
                          (!geglu || d.N % 64 == 0);
     // Non-persistent kernel (2 CTAs/SM, two interleaved MMA streams) is measurably faster for the long-reduction,
     // wide-N convolutions (profiles/r01_kbench_ab_experiments.txt); the persistent one wins everywhere else.
-    const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu;
+    const bool v2_only = d.colscale != nullptr || (d.flags & TG_GELU_TANH);
+    if (v2_only && !aligned) return fail("tapgemm: colscale / tanh-GELU epilogues need N %% 32 == 0 and 16-byte aligned rows");
+    const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu && !v2_only;
     if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
         if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm2_bn<160>(d, st);
         return launch_tapgemm2_bn<128>(d, st);
@@ -312,6 +315,12 @@ int star_init(int device) {
 int star_linear(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
                 long long rowvec_div, const void* residual, long long ldres, void* out, long long ldo,
                 long long rows, int K, int N, int flags, void* stream) {
+    return star_linear_ex(A, lda, W, bias, rowvec, rowvec_div, nullptr, residual, ldres, out, ldo, rows, K, N, flags, stream);
+}
+
+int star_linear_ex(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
+                   long long rowvec_div, const void* colscale, const void* residual, long long ldres, void* out,
+                   long long ldo, long long rows, int K, int N, int flags, void* stream) {
     STAR_CHECK_INIT();
     if (rows <= 0) return 0;
     if (K % 8 || lda % 8) return fail("star_linear: K and lda must be multiples of 8 (K=%d lda=%lld)", K, lda);
@@ -326,6 +335,7 @@ int star_linear(const void* A, long long lda, const void* W, const void* bias, c
     d.ntaps = 1;
     d.K = K; d.N = N; d.flags = flags;
     d.W = W; d.bias = bias; d.rowvec = rowvec; d.rowvec_div = rowvec_div; d.residual = residual; d.ldres = ldres;
+    d.colscale = colscale;
     d.out = out; d.ldo = ldo;
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
@@ -563,7 +573,7 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
 
 int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,
                    int gate_mode, const void* gate, float w0, float w1, void* stream) {
-    if (C % 8 || C / 8 > 32 * LN_MAX_OCT) return fail("star_layernorm: unsupported C=%d", C);
+    if (C % 8 || C / 8 > 32 * 12) return fail("star_layernorm: unsupported C=%d", C);
     const int wpb = 8;
     const long long want = (rows + wpb - 1) / wpb;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 6);
@@ -574,7 +584,8 @@ int star_layernorm(const void* X, const void* gamma, const void* beta, void* out
                                                                      gate_mode, (const __half*)gate, w0, w1)
     if (oct <= 2) STAR_LN_LAUNCH(2);
     else if (oct <= 3) STAR_LN_LAUNCH(3);
-    else STAR_LN_LAUNCH(5);
+    else if (oct <= 5) STAR_LN_LAUNCH(5);
+    else STAR_LN_LAUNCH(12);
 #undef STAR_LN_LAUNCH
     STAR_LAUNCH_CHECK("layernorm");
     return 0;
@@ -590,6 +601,28 @@ int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* ga
     liem_conv7_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __half*)mm_ws, (const __half*)w98, (__half*)gate,
                                                                        BT, H, W);
     STAR_LAUNCH_CHECK("liem_conv7");
+    return 0;
+}
+
+int star_row_gate(const void* X, void* out, long long rows, int C, int mode, const void* gate, float w0, float w1,
+                  void* stream) {
+    if (C % 8) return fail("star_row_gate: C must be a multiple of 8");
+    if (mode != 1 && mode != 2) return fail("star_row_gate: mode must be 1 (external gate) or 2 (temporal LIEM)");
+    const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, (long long)g_num_sms * 8);
+    row_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, rows, C, mode, (const __half*)gate, w0, w1);
+    STAR_LAUNCH_CHECK("row_gate");
+    return 0;
+}
+
+int star_qk_ln_rope(void* QKV, long long ld, long long rows, int heads, int koff, const void* qg, const void* qb,
+                    const void* kg, const void* kb, const void* cos_f32, const void* sin_f32, int seq, int text_len,
+                    float eps, void* stream) {
+    if (ld % 8 || koff % 8) return fail("star_qk_ln_rope: ld and koff must be multiples of 8");
+    const long long threads = rows * heads * 2 * 8;
+    qk_ln_rope_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (__half*)QKV, ld, rows, heads, koff, (const __half*)qg, (const __half*)qb, (const __half*)kg, (const __half*)kb,
+        (const float*)cos_f32, (const float*)sin_f32, seq, text_len, eps);
+    STAR_LAUNCH_CHECK("qk_ln_rope");
     return 0;
 }
 

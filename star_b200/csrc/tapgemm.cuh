@@ -29,7 +29,7 @@ constexpr int TG_THREADS = 192;
 enum TapGemmFlags : int {
     TG_GEGLU = 1,        // W has 2N rows (value | gate); out = value * gelu_erf(gate)
     TG_SILU_OUT = 2,     // out = silu(acc)
-    TG_GELU_LIBM = 4,    // debug: libdevice erff instead of erf_as in the GEGLU epilogue
+    TG_GELU_TANH = 8,    // out = gelu_tanh(acc)  (CogVideoX MLP, sat default gelu)
 };
 
 struct TapGemmParams {
@@ -46,6 +46,7 @@ struct TapGemmParams {
     const __half* bias;   // [N] ([2N] with GEGLU) or null
     const __half* rowvec; // [rows_out / rowvec_div, N] or null  (time-embedding add, unet_v2v.py:684)
     int rowvec_div;
+    const __half* colscale;   // [N] or null: acc = colscale[n] * (acc + bias[n]) before the residual add (adaLN gate)
     const __half* residual;   // [rows_out, res_ld] or null
     long long res_ld;
     __half* out;

@@ -264,6 +264,21 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }
+                if (p.flags & TG_GELU_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_f(f[j]);
+                }
+                if (p.colscale) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (n0 + u * 8 + 8 <= p.N) {
+                            float cs[8];
+                            unpack8h(__ldg(reinterpret_cast<const uint4*>(p.colscale + n0 + u * 8)), cs);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[u * 8 + e] *= cs[e];
+                        }
+                    }
+                }
                 if (rv_row) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {

@@ -19,6 +19,9 @@ SIGNATURES = {
     "star_launch_count": (_ll, []),
     "star_init": (_i, [_i]),
     "star_linear": (_i, [_p, _ll, _p, _p, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "star_linear_ex": (_i, [_p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "star_row_gate": (_i, [_p, _p, _ll, _i, _i, _p, _f, _f, _p]),
+    "star_qk_ln_rope": (_i, [_p, _ll, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p]),
     "star_conv2d_3x3": (_i, [_p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p]),
     "star_conv2d_s2_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "star_conv2d_3x3_s2": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _p]),

@@ -304,3 +304,47 @@ def silu(x):
     L = _L.get_lib()
     _L.check(L.star_silu(_p(x), _p(out), x.numel(), _st()), "star_silu")
     return out
+
+
+FLAG_GELU_TANH = 8
+
+
+@_traced
+def linear_ex(a, w, bias=None, colscale=None, residual=None, flags=0, out=None):
+    """out = residual + colscale[n] * act(sum_k a[r,k] w[n,k] + bias[n])   (adaLN-gated residual, tanh-GELU option)"""
+    _dev(a)
+    lda = _rowmajor(a, "a")
+    rows, K = a.shape
+    N = w.shape[0]
+    assert w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        out = torch.empty((rows, N), dtype=HALF, device=a.device)
+    ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    L = _L.get_lib()
+    _L.check(L.star_linear_ex(_p(a), lda, _p(w), _p(bias), None, 1, _p(colscale), _p(residual), ldres, _p(out),
+                              _rowmajor(out, "out"), rows, K, N, flags, _st()), "star_linear_ex")
+    return out
+
+
+@_traced
+def row_gate(x, mode, gate=None, w0=0.0, w1=0.0, out=None):
+    _dev(x)
+    rows, C = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    L = _L.get_lib()
+    _L.check(L.star_row_gate(_p(x), _p(out), rows, C, mode, _p(gate), float(w0), float(w1), _st()), "star_row_gate")
+    return out
+
+
+@_traced
+def qk_ln_rope(qkv, heads, koff, qg, qb, kg, kb, cos, sin, seq, text_len, eps=1e-6):
+    """in place on qkv [rows, ld]"""
+    _dev(qkv)
+    ld = _rowmajor(qkv, "qkv")
+    assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+    L = _L.get_lib()
+    _L.check(L.star_qk_ln_rope(_p(qkv), ld, qkv.shape[0], heads, koff, _p(qg), _p(qb), _p(kg), _p(kb), _p(cos), _p(sin),
+                               seq, text_len, float(eps), _st()), "star_qk_ln_rope")
+    return qkv

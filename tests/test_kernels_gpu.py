@@ -215,3 +215,43 @@ def test_copies(env):
     t = torch.tensor([899, 34], device="cuda")
     assert_close(O.sinusoidal(t, 320), R.sinusoidal(t, 320), rel=2e-3, what="sinusoidal")
     assert_close(O.silu(a), R.silu(a), what="silu")
+
+
+# ---- CogVideoX DiT helpers -------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,K,N,flags,extras", [(322, 3072, 3072, 0, "bias,cs,res"), (700, 320, 1280, 8, "bias"),
+                                                   (226, 1024, 640, 8, "bias,cs,res")])
+def test_linear_ex(env, rows, K, N, flags, extras):
+    O, R = env
+    a = rnd(rows, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, scale=0.1) if "bias" in extras else None
+    cs = rnd(N, seed=4) if "cs" in extras else None
+    res = rnd(rows, N, seed=5) if "res" in extras else None
+    got = O.linear_ex(a, w, bias, cs, res, flags)
+    torch.cuda.synchronize()
+    assert_close(got, R.linear_ex(a, w, bias, cs, res, flags), what=f"linear_ex {rows}x{K}x{N} flags={flags} {extras}")
+
+
+def test_layernorm_wide(env):
+    O, R = env
+    x = rnd(500, 3072, seed=1)
+    g, b = (1 + 0.1 * torch.randn(3072, device="cuda")).half(), (0.1 * torch.randn(3072, device="cuda")).half()
+    assert_close(O.layernorm(x, g, b), R.layernorm(x, g, b), what="layernorm C=3072")
+
+
+def test_row_gate_and_qk_ln_rope(env):
+    O, R = env
+    x = rnd(333, 3072, seed=1)
+    gate = torch.rand(333, device="cuda").half()
+    assert_close(O.row_gate(x, 1, gate), R.row_gate(x, 1, gate), what="row_gate ext")
+    assert_close(O.row_gate(x, 2, None, 0.4, -0.3), R.row_gate(x, 2, None, 0.4, -0.3), what="row_gate temporal")
+    heads, seq, tl = 6, 50, 10
+    qkv = rnd(2 * seq, 3 * heads * 64, seed=2)
+    ref_in = qkv.clone()
+    qg, qb, kg, kb = (rnd(64, seed=s, scale=0.5) + (1 if s % 2 == 0 else 0) for s in (10, 11, 12, 13))
+    ang = torch.rand(seq - tl, 64, device="cuda") * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    O.qk_ln_rope(qkv, heads, heads * 64, qg, qb, kg, kb, cos, sin, seq, tl, 1e-6)
+    torch.cuda.synchronize()
+    R.qk_ln_rope(ref_in, heads, heads * 64, qg, qb, kg, kb, cos, sin, seq, tl, 1e-6)
+    assert_close(qkv, ref_in, what="qk_ln_rope")
