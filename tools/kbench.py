@@ -82,6 +82,12 @@ def bench_linear():
     R = F * H * W
     a, w, bias = rnd(R, C), rnd(3 * C, C, scale=C ** -0.5), None
     report("linear L2 qkv (1280->3840)", timeit(lambda: O.linear(a, w)), flops=2.0 * R * C * 3 * C)
+    for lvl in (1, 2):
+        H, W, C = LEVELS[lvl]
+        R = F * H * W
+        a, w, bias = rnd(R, C), rnd(8 * C, C, scale=C ** -0.5), rnd(8 * C, scale=0.1)
+        report(f"linear L{lvl} FF in GEGLU ({C}->2x{4 * C})", timeit(lambda: O.linear(a, w, bias, None, None, 1, 1)),
+               flops=2.0 * R * C * 8 * C)
 
 
 def bench_conv():
