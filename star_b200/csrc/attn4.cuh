@@ -102,13 +102,18 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);
+            // descriptors are built once; a stage / k-step is a 64-bit add (the issuing threads are on the critical path)
+            const uint64_t dq0 = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_Q), 16, 1024);
+            const uint64_t dk0 = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_K), 16, 1024);
+            const uint64_t dv0 = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_V), 8192, 1024);
+            constexpr uint64_t TILE_INC = (uint64_t)(Attn4Smem::TILE >> 4);
             auto issue_s = [&](int t, int j) {
-                const uint32_t q_addr = smem_u32(smem + Attn4Smem::OFF_Q + t * Attn4Smem::TILE);
-                const uint32_t k_addr = smem_u32(smem + Attn4Smem::OFF_K + (j % A4_KV_STAGES) * Attn4Smem::TILE);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16_ss(tmem_base + t * 128, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                                umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                const uint64_t dq = dq0 + TILE_INC * (uint64_t)t;
+                const uint64_t dk = dk0 + TILE_INC * (uint64_t)(j % A4_KV_STAGES);
+                umma_f16_ss(tmem_base + t * 128, dq, dk, idesc_s, 0u);
+                umma_f16_ss(tmem_base + t * 128, dq + 2, dk + 2, idesc_s, 1u);
+                umma_f16_ss(tmem_base + t * 128, dq + 4, dk + 4, idesc_s, 1u);
+                umma_f16_ss(tmem_base + t * 128, dq + 6, dk + 6, idesc_s, 1u);
                 umma_commit(&s_full[t]);
             };
             mbar_wait(q_full, 0);
@@ -118,11 +123,11 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             auto issue_pv = [&](int t, int j) {
                 mbar_wait(&p_full[t], j & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + (j % A4_KV_STAGES) * Attn4Smem::TILE);
+                const uint64_t dv = dv0 + TILE_INC * (uint64_t)(j % A4_KV_STAGES);
+                const uint32_t d_o = tmem_base + 256 + t * 64, a_p = tmem_base + 384 + t * 64;
 #pragma unroll
                 for (int k = 0; k < 8; ++k)             // A = P_t (TMEM, 8 columns = 16 fp16 keys per step), B = V (MN-major)
-                    umma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
-                                umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_ts(d_o, a_p + k * 8, dv + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&pv_done[t]);
             };
             auto next_s = [&](int t, int j) {           // S_t(j+1) as soon as S_t(j) sits in the softmax registers
@@ -176,13 +181,16 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // second MMA-issuing thread: query tile 1
             constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);
-            const uint32_t q_addr = smem_u32(smem + Attn4Smem::OFF_Q + Attn4Smem::TILE);
+            const uint64_t dq = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_Q + Attn4Smem::TILE), 16, 1024);
+            const uint64_t dk0 = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_K), 16, 1024);
+            const uint64_t dv0 = umma_desc_sw128(smem_u32(smem + Attn4Smem::OFF_V), 8192, 1024);
+            constexpr uint64_t TILE_INC = (uint64_t)(Attn4Smem::TILE >> 4);
             auto issue_s1 = [&](int j) {
-                const uint32_t k_addr = smem_u32(smem + Attn4Smem::OFF_K + (j % A4_KV_STAGES) * Attn4Smem::TILE);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16_ss(tmem_base + 128, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                                umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                const uint64_t dk = dk0 + TILE_INC * (uint64_t)(j % A4_KV_STAGES);
+                umma_f16_ss(tmem_base + 128, dq, dk, idesc_s, 0u);
+                umma_f16_ss(tmem_base + 128, dq + 2, dk + 2, idesc_s, 1u);
+                umma_f16_ss(tmem_base + 128, dq + 4, dk + 4, idesc_s, 1u);
+                umma_f16_ss(tmem_base + 128, dq + 6, dk + 6, idesc_s, 1u);
                 umma_commit(&s_full[1]);
             };
             mbar_wait(q_full, 0);
@@ -198,11 +206,11 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + Attn4Smem::OFF_V + (j % A4_KV_STAGES) * Attn4Smem::TILE);
+                const uint64_t dv = dv0 + TILE_INC * (uint64_t)(j % A4_KV_STAGES);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_f16_ts(tmem_base + 256 + 64, tmem_base + 384 + 64 + k * 8,
-                                umma_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_ts(tmem_base + 256 + 64, tmem_base + 384 + 64 + k * 8, dv + (uint64_t)(k * 128), idesc_o,
+                                (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&pv_done[1]);
                 umma_commit(&kv_empty[j % A4_KV_STAGES]);
             }

@@ -118,7 +118,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int c1 = org[0] + p.tap[t][0], c2 = org[1] + p.tap[t][1];
                 const int c3 = org[2] + p.tap[t][2], c4 = org[3] + p.tap[t][3];
                 for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                    const int s = it % TG_STAGES;
+                    const int s = it % TG_STAGES;                 // compile-time modulus (3)
                     const uint32_t ph = (it / TG_STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * SM::STAGE_BYTES;
@@ -139,20 +139,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(TG_BM, BN, 0, 0);
+            const uint64_t desc_a0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+            const uint64_t desc_b0 = umma_desc_sw128(smem_u32(smem) + SM::A_BYTES, 16, 1024);
+            constexpr uint64_t STAGE_INC = (uint64_t)(SM::STAGE_BYTES >> 4);
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < total_iters; ++it) {
-                const int s = it % TG_STAGES;
-                const uint32_t ph = (it / TG_STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + SM::A_BYTES;
-#pragma unroll
-                for (int k = 0; k < TG_BK / 16; ++k) {
-                    const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-                    const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                    umma_f16_ss(tmem_acc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                }
+                const uint64_t da = desc_a0 + STAGE_INC * (uint64_t)s;
+                const uint64_t db = desc_b0 + STAGE_INC * (uint64_t)s;
+                umma_f16_ss(tmem_acc, da, db, idesc, it > 0 ? 1u : 0u);
+                umma_f16_ss(tmem_acc, da + 2, db + 2, idesc, 1u);
+                umma_f16_ss(tmem_acc, da + 4, db + 4, idesc, 1u);
+                umma_f16_ss(tmem_acc, da + 6, db + 6, idesc, 1u);
                 umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+                if (++s == TG_STAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(acc_bar);                    // accumulator complete
         }
