@@ -56,6 +56,13 @@ int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void*
 long long star_conv2d_s2_workspace_bytes(int BT, int H, int W, int Cin);
 int star_conv2d_3x3_s2(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
                        int BT, int H, int W, int Cin, int Cout, void* stream);
+/* Same with explicit zero padding (top, bottom, left, right): the temporal VAE's encoder downsamples with
+ * F.pad(x, (0,1,0,1)) + Conv2d(stride 2, padding 0) (diffusers 0.30.0 Downsample2D, reached from
+ * video_to_video_model.py:158 vae.encode).  Ho = (H+pad_t+pad_b-3)/2 + 1, Wo likewise. */
+long long star_conv2d_s2p_workspace_bytes(int BT, int H, int W, int Cin, int pad_t, int pad_b, int pad_l, int pad_r);
+int star_conv2d_3x3_s2p(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
+                        int BT, int H, int W, int Cin, int Cout, int pad_t, int pad_b, int pad_l, int pad_r,
+                        void* stream);
 /* Conv3d (3,1,1) pad (1,0,0) over frames on X[B,T,HW,Cin]; W3 = weight permuted to [Cout][3][Cin]
  * (unet_v2v.py:1209-1220). */
 int star_conv_t3(const void* X, const void* W3, const void* bias, const void* residual, long long ldres, void* out,
@@ -108,6 +115,19 @@ int star_concat_add(const void* a, int Ca, const void* b, const void* c, int Cb,
 int star_add(const void* a, const void* b, void* out, long long n, void* stream);
 /* nearest x2 + crop first/last row (unet_v2v.py:563-564): out [BT, 2H-2, 2W, C] */
 int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, void* stream);
+/* nearest x2, crop_rows = 1 as above, 0 = plain F.interpolate(scale_factor=2) of the VAE decoder's Upsample2D
+ * (video_to_video_model.py:142 vae.decode): out [BT, 2H - 2*crop_rows, 2W, C] */
+int star_upsample2x(const void* X, void* out, int BT, int H, int W, int C, int crop_rows, void* stream);
+
+/* ---- temporal VAE (video_to_video_model.py:141-161 -> diffusers AutoencoderKLTemporalDecoder) ----------------
+ * The single-head (d = 512) mid-block attention runs as S = Q K^T (star_linear, N = tokens), star_softmax_rows,
+ * O = S V (star_linear against V^T).  star_softmax_rows: in place over the first `cols` entries of each
+ * 16-byte-aligned row of the fp16 matrix S[rows, ld] (logits already scaled), columns cols..ld-1 zeroed. */
+int star_softmax_rows(void* S, long long ld, long long rows, int cols, void* stream);
+/* decoder tail: time_conv_out = Conv3d(3,3,(3,1,1),padding (1,0,0)) over X[(b t hw), ldx] (3 valid channels) fused with
+ * the tokens -> (b t, 3, h, w) layout change; W27 = weight [3][3][3] (co, ci, dt) fp16, bias3 fp16, out fp16. */
+int star_vae_head(const void* X, long long ldx, const void* W27, const void* bias3, void* out, int B, int T,
+                  long long HW, void* stream);
 /* (b,c,f,h,w) fp32 -> tokens fp16 [(b f h w), c]  and back (fp16 -> fp16)  (unet_v2v.py:1772,:1808) */
 int star_nchw5_to_tokens(const void* x_f32, void* out, int B, int C, int F, long long HW, void* stream);
 int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, int F, long long HW, void* stream);

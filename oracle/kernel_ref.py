@@ -116,13 +116,17 @@ def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
     return o.permute(0, 3, 1, 2, 4).reshape(B * T * HW, Ci).to(HALF)
 
 
-def groupnorm(x, gamma, beta, nsamples, eps, silu):
+def groupnorm(x, gamma, beta, nsamples, eps, silu, out=None):
     rows, C = x.shape
     xs = _f(x).reshape(nsamples, rows // nsamples, C).permute(0, 2, 1)          # n c r
     y = F.group_norm(xs, 32, _f(gamma), _f(beta), eps)
     if silu:
         y = F.silu(y)
-    return y.permute(0, 2, 1).reshape(rows, C).to(HALF)
+    res = y.permute(0, 2, 1).reshape(rows, C).to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
@@ -233,3 +237,31 @@ def qk_ln_rope(qkv, heads, koff, qg, qb, kg, kb, cos, sin, seq, text_len, eps=1e
         y = torch.where(img[:, None, None], x * c + rot * s, x)
         qkv[:, off:off + heads * 64] = y.reshape(rows, heads * 64).to(HALF)
     return qkv
+
+
+def conv2d_3x3_s2p(x, w9, bias=None, pad=(0, 1, 0, 1)):
+    BT, H, W, Cin = x.shape
+    pt, pb, pl, pr = pad
+    xp = F.pad(_f(x).permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    y = F.conv2d(xp, _f(w9).permute(0, 3, 1, 2), _f(bias), stride=2)
+    Ho, Wo = y.shape[2], y.shape[3]
+    return y.permute(0, 2, 3, 1).reshape(BT * Ho * Wo, -1).to(HALF), Ho, Wo
+
+
+def upsample2x(x, BT, H, W):
+    C = x.shape[1]
+    up = x.reshape(BT, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    return up.reshape(-1, C).contiguous()
+
+
+def softmax_rows(s, cols):
+    p = torch.softmax(_f(s[:, :cols]), dim=-1).to(HALF)
+    s.zero_()
+    s[:, :cols] = p
+    return s
+
+
+def vae_head(x, w27, bias3, B, T, H, W):
+    x5 = _f(x[:, :3]).reshape(B, T, H, W, 3).permute(0, 4, 1, 2, 3)                 # b c t h w
+    y = F.conv3d(x5, _f(w27).reshape(3, 3, 3, 1, 1), _f(bias3), padding=(1, 0, 0))
+    return y.permute(0, 2, 1, 3, 4).reshape(B * T, 3, H, W).to(HALF)

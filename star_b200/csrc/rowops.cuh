@@ -572,9 +572,10 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
     }
 }
 // nearest x2 upsample then drop the first and last row (unet_v2v.py:563-564): out H' = 2H-2, W' = 2W
+// crop = 0: plain nearest x2 (the VAE decoder's Upsample2D), out H' = 2H
 __global__ void upsample2x_crop_kernel(const __half* __restrict__ x, __half* __restrict__ out, int BT, int H, int W,
-                                       int C) {
-    const int O = C / 8, Ho = 2 * H - 2, Wo = 2 * W;
+                                       int C, int crop) {
+    const int O = C / 8, Ho = 2 * H - 2 * crop, Wo = 2 * W;
     const long long n = (long long)BT * Ho * Wo * O;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int oc = (int)(i % O);
@@ -582,15 +583,16 @@ __global__ void upsample2x_crop_kernel(const __half* __restrict__ x, __half* __r
         const int ow = (int)(t % Wo); t /= Wo;
         const int oh = (int)(t % Ho);
         const long long bt = t / Ho;
-        const int ih = (oh + 1) >> 1, iw = ow >> 1;
+        const int ih = (oh + crop) >> 1, iw = ow >> 1;
         reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(x + ((bt * H + ih) * W + iw) * C + oc * 8));
     }
 }
 // stride-2 conv input split (unet_v2v.py:709: stride 2, padding (2,1)):
 // planes[bt][pq][i][j][:] = Xpad[2i + p][2j + q],  Xpad = X zero-padded by 2 rows / 1 column on each side,
 // pq = 2p + q, plane extent (Ho+1, Wo+1) with Ho = (H+1)/2 + 1... computed by the host.
+// pad_t / pad_l: zero rows / columns in front (2, 1 for the UNet; 0, 0 for the VAE encoder's pad (0,1,0,1)).
 __global__ void s2_split_kernel(const __half* __restrict__ x, __half* __restrict__ planes, int BT, int H, int W, int C,
-                                int H2, int W2) {
+                                int H2, int W2, int pad_t, int pad_l) {
     const int O = C / 8;
     const long long n = (long long)BT * 4 * H2 * W2 * O;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -600,13 +602,95 @@ __global__ void s2_split_kernel(const __half* __restrict__ x, __half* __restrict
         const int i = (int)(t % H2); t /= H2;
         const int pq = (int)(t % 4);
         const long long bt = t / 4;
-        const int ih = 2 * i + (pq >> 1) - 2, iw = 2 * j + (pq & 1) - 1;
+        const int ih = 2 * i + (pq >> 1) - pad_t, iw = 2 * j + (pq & 1) - pad_l;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (ih >= 0 && ih < H && iw >= 0 && iw < W)
             v = __ldg(reinterpret_cast<const uint4*>(x + ((bt * H + ih) * W + iw) * C + oc * 8));
         reinterpret_cast<uint4*>(planes)[idx] = v;
     }
 }
+// ------------------------------------------------------------------ single-head attention pieces (VAE mid block)
+// In-place softmax over the first `cols` entries of each row of S[rows, ld] (fp16 logits, already scaled);
+// one CTA per row, the row staged in shared memory, statistics in fp32.  Columns cols..ld-1 are zeroed.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(__half* __restrict__ S, long long ld, int cols) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* row_s = reinterpret_cast<__half*>(sm_raw);
+    __shared__ float red[8];
+    __half* row = S + (long long)blockIdx.x * ld;
+    const int tid = threadIdx.x, nv = cols / 8;
+    float mx = -INFINITY;
+    for (int i = tid; i < nv; i += 256) {
+        const uint4 u = reinterpret_cast<const uint4*>(row)[i];
+        reinterpret_cast<uint4*>(row_s)[i] = u;
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    }
+    for (int i = nv * 8 + tid; i < cols; i += 256) {
+        const __half h = row[i];
+        row_s[i] = h;
+        mx = fmaxf(mx, __half2float(h));
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = tid; i < cols; i += 256) sum += __expf(__half2float(row_s[i]) - mx);
+    sum = warp_sum(sum);
+    if ((tid & 31) == 0) red[tid >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    const float inv = 1.f / sum;
+    for (int i = tid; i < nv; i += 256) {
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(row_s)[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx) * inv;
+        reinterpret_cast<uint4*>(row)[i] = pack8(f);
+    }
+    for (long long i = nv * 8 + tid; i < ld; i += 256)
+        row[i] = i < cols ? __float2half_rn(__expf(__half2float(row_s[i]) - mx) * inv) : __float2half_rn(0.f);
+}
+
+// ------------------------------------------------------------------ VAE decoder head
+// time_conv_out: Conv3d(3 -> 3, kernel (3,1,1), padding (1,0,0)) over the frames of x[(b t hw), ldx] (3 valid
+// channels) fused with the tokens -> (b t) c h w conversion; w[co][ci][dt], fp16 output.
+__global__ void vae_head_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ w16,
+                                const __half* __restrict__ bias16, __half* __restrict__ out, int B, int T, long long HW) {
+    float w[27], bias[3];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) w[k] = __half2float(w16[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bias[k] = bias16 ? __half2float(bias16[k]) : 0.f;
+    const long long n = (long long)B * T * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long hw = i % HW;
+        const long long bt = i / HW;
+        const int t = (int)(bt % T);
+        float acc[3] = {bias[0], bias[1], bias[2]};
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            const int tt = t + dt - 1;
+            if (tt < 0 || tt >= T) continue;
+            const __half* xr = x + (i + (long long)(dt - 1) * HW) * ldx;
+            const float x0 = __half2float(xr[0]), x1 = __half2float(xr[1]), x2 = __half2float(xr[2]);
+#pragma unroll
+            for (int co = 0; co < 3; ++co)
+                acc[co] += w[(co * 3 + 0) * 3 + dt] * x0 + w[(co * 3 + 1) * 3 + dt] * x1 + w[(co * 3 + 2) * 3 + dt] * x2;
+        }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) out[(bt * 3 + co) * HW + hw] = __float2half_rn(acc[co]);
+    }
+}
+
 // sinusoidal timestep embedding cos || sin (unet_v2v.py:96-108) -> fp16 [B, dim]
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, __half* __restrict__ out, int B, int dim) {
     const int half_d = dim / 2;

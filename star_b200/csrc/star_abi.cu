@@ -367,19 +367,31 @@ int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void*
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
 
-long long star_conv2d_s2_workspace_bytes(int BT, int H, int W, int Cin) {
-    const long long Ho = (H + 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+long long star_conv2d_s2p_workspace_bytes(int BT, int H, int W, int Cin, int pad_t, int pad_b, int pad_l, int pad_r) {
+    const long long Ho = (H + pad_t + pad_b - 3) / 2 + 1, Wo = (W + pad_l + pad_r - 3) / 2 + 1;
     return (long long)BT * 4 * (Ho + 1) * (Wo + 1) * Cin * 2;
+}
+
+long long star_conv2d_s2_workspace_bytes(int BT, int H, int W, int Cin) {
+    return star_conv2d_s2p_workspace_bytes(BT, H, W, Cin, 2, 2, 1, 1);
 }
 
 int star_conv2d_3x3_s2(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
                        int BT, int H, int W, int Cin, int Cout, void* stream) {
+    return star_conv2d_3x3_s2p(X, W9, bias, out, ldo, planes_ws, BT, H, W, Cin, Cout, 2, 2, 1, 1, stream);
+}
+
+int star_conv2d_3x3_s2p(const void* X, const void* W9, const void* bias, void* out, long long ldo, void* planes_ws,
+                        int BT, int H, int W, int Cin, int Cout, int pad_t, int pad_b, int pad_l, int pad_r,
+                        void* stream) {
     STAR_CHECK_INIT();
-    if (Cin % 8) return fail("star_conv2d_3x3_s2: Cin must be a multiple of 8");
-    const int Ho = (H + 1) / 2 + 1, Wo = (W - 1) / 2 + 1, H2 = Ho + 1, W2 = Wo + 1;
+    if (Cin % 8) return fail("star_conv2d_3x3_s2p: Cin must be a multiple of 8");
+    if (pad_t < 0 || pad_b < 0 || pad_l < 0 || pad_r < 0 || H + pad_t + pad_b < 3 || W + pad_l + pad_r < 3)
+        return fail("star_conv2d_3x3_s2p: bad padding");
+    const int Ho = (H + pad_t + pad_b - 3) / 2 + 1, Wo = (W + pad_l + pad_r - 3) / 2 + 1, H2 = Ho + 1, W2 = Wo + 1;
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)BT * 4 * H2 * W2 * (Cin / 8);
-    s2_split_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)X, (__half*)planes_ws, BT, H, W, Cin, H2, W2);
+    s2_split_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)X, (__half*)planes_ws, BT, H, W, Cin, H2, W2, pad_t, pad_l);
     STAR_LAUNCH_CHECK("s2_split");
     TapDesc d;
     memset(&d, 0, sizeof(d));
@@ -643,11 +655,43 @@ int star_add(const void* a, const void* b, void* out, long long n, void* stream)
     return 0;
 }
 
+int star_upsample2x(const void* X, void* out, int BT, int H, int W, int C, int crop_rows, void* stream) {
+    if (C % 8) return fail("star_upsample2x: C must be a multiple of 8");
+    if (crop_rows != 0 && crop_rows != 1) return fail("star_upsample2x: crop_rows must be 0 or 1");
+    const long long n = (long long)BT * (2 * H - 2 * crop_rows) * (2 * W) * (C / 8);
+    upsample2x_crop_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, BT, H, W, C, crop_rows);
+    STAR_LAUNCH_CHECK("upsample2x");
+    return 0;
+}
+
 int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, void* stream) {
-    if (C % 8) return fail("star_upsample2x_crop: C must be a multiple of 8");
-    const long long n = (long long)BT * (2 * H - 2) * (2 * W) * (C / 8);
-    upsample2x_crop_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, BT, H, W, C);
-    STAR_LAUNCH_CHECK("upsample2x_crop");
+    return star_upsample2x(X, out, BT, H, W, C, 1, stream);
+}
+
+int star_softmax_rows(void* S, long long ld, long long rows, int cols, void* stream) {
+    if (rows <= 0) return 0;
+    if (ld % 8 || reinterpret_cast<uintptr_t>(S) % 16) return fail("star_softmax_rows: rows must be 16-byte aligned (ld %% 8 == 0)");
+    if (cols <= 0 || cols > ld) return fail("star_softmax_rows: need 0 < cols <= ld");
+    const size_t smem = ((size_t)cols * 2 + 15) / 16 * 16;
+    if (smem > 200 * 1024) return fail("star_softmax_rows: %d columns do not fit in shared memory", cols);
+    if (rows > 0x7fffffffll) return fail("star_softmax_rows: too many rows");
+    static bool attr_set = false;
+    if (!attr_set) {
+        STAR_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    softmax_rows_kernel<<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>((__half*)S, ld, cols);
+    STAR_LAUNCH_CHECK("softmax_rows");
+    return 0;
+}
+
+int star_vae_head(const void* X, long long ldx, const void* W27, const void* bias3, void* out, int B, int T,
+                  long long HW, void* stream) {
+    if (ldx < 3) return fail("star_vae_head: ldx must be >= 3");
+    const long long n = (long long)B * T * HW;
+    vae_head_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, ldx, (const __half*)W27,
+                                                                        (const __half*)bias3, (__half*)out, B, T, HW);
+    STAR_LAUNCH_CHECK("vae_head");
     return 0;
 }
 

@@ -37,6 +37,11 @@ SIGNATURES = {
     "star_concat_add": (_i, [_p, _i, _p, _p, _i, _p, _ll, _p]),
     "star_add": (_i, [_p, _p, _p, _ll, _p]),
     "star_upsample2x_crop": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "star_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "star_softmax_rows": (_i, [_p, _ll, _ll, _i, _p]),
+    "star_vae_head": (_i, [_p, _ll, _p, _p, _p, _i, _i, _ll, _p]),
+    "star_conv2d_s2p_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "star_conv2d_3x3_s2p": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "star_nchw5_to_tokens": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
     "star_tokens_to_nchw5": (_i, [_p, _ll, _p, _i, _i, _i, _ll, _p]),
     "star_sinusoidal": (_i, [_p, _p, _i, _i, _p]),

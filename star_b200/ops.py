@@ -140,6 +140,23 @@ def conv2d_3x3_s2(x, w9, bias=None):
 
 
 @_traced
+def conv2d_3x3_s2p(x, w9, bias=None, pad=(0, 1, 0, 1)):
+    """Stride-2 3x3 conv with explicit zero padding pad = (top, bottom, left, right).  Returns (out, Ho, Wo)."""
+    _dev(x)
+    BT, H, W, Cin = x.shape
+    Cout = w9.shape[0]
+    assert x.is_contiguous() and w9.is_contiguous()
+    pt, pb, pl, pr = (int(v) for v in pad)
+    Ho, Wo = (H + pt + pb - 3) // 2 + 1, (W + pl + pr - 3) // 2 + 1
+    L = _L.get_lib()
+    ws = torch.empty(L.star_conv2d_s2p_workspace_bytes(BT, H, W, Cin, pt, pb, pl, pr), dtype=torch.uint8, device=x.device)
+    out = torch.empty((BT * Ho * Wo, Cout), dtype=HALF, device=x.device)
+    _L.check(L.star_conv2d_3x3_s2p(_p(x), _p(w9), _p(bias), _p(out), Cout, _p(ws), BT, H, W, Cin, Cout, pt, pb, pl, pr,
+                                   _st()), "star_conv2d_3x3_s2p")
+    return out, Ho, Wo
+
+
+@_traced
 def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
     """Temporal conv (3,1,1): x [B*T*HW, Cin]; w3 [Cout, 3, Cin]."""
     _dev(x)
@@ -195,14 +212,16 @@ def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
 
 
 @_traced
-def groupnorm(x, gamma, beta, nsamples, eps, silu):
-    """x [rows, C]; nsamples equal blocks of rows share statistics."""
+def groupnorm(x, gamma, beta, nsamples, eps, silu, out=None):
+    """x [rows, C]; nsamples equal blocks of rows share statistics.  out may alias x (in place)."""
     _dev(x)
     rows, C = x.shape
     assert x.is_contiguous() and rows % nsamples == 0
     L = _L.get_lib()
     ws = torch.empty(L.star_groupnorm_workspace_bytes(nsamples, C), dtype=torch.uint8, device=x.device)
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape
     _L.check(L.star_groupnorm(_p(x), _p(gamma), _p(beta), _p(out), nsamples, rows // nsamples, C, float(eps),
                               int(bool(silu)), _p(ws), _st()), "star_groupnorm")
     return out
@@ -262,6 +281,41 @@ def upsample2x_crop(x, BT, H, W):
     out = torch.empty((BT * (2 * H - 2) * (2 * W), C), dtype=HALF, device=x.device)
     L = _L.get_lib()
     _L.check(L.star_upsample2x_crop(_p(x), _p(out), BT, H, W, C, _st()), "star_upsample2x_crop")
+    return out
+
+
+@_traced
+def upsample2x(x, BT, H, W):
+    """plain nearest x2: [BT*H*W, C] -> [BT*2H*2W, C]"""
+    _dev(x)
+    C = x.shape[1]
+    assert x.is_contiguous()
+    out = torch.empty((BT * 4 * H * W, C), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_upsample2x(_p(x), _p(out), BT, H, W, C, 0, _st()), "star_upsample2x")
+    return out
+
+
+@_traced
+def softmax_rows(s, cols):
+    """in-place row softmax of the fp16 matrix s[rows, ld] over its first `cols` columns"""
+    _dev(s)
+    ld = _rowmajor(s, "s")
+    L = _L.get_lib()
+    _L.check(L.star_softmax_rows(_p(s), ld, s.shape[0], int(cols), _st()), "star_softmax_rows")
+    return s
+
+
+@_traced
+def vae_head(x, w27, bias3, B, T, H, W):
+    """x [(b t h w), ld>=3] -> (B*T, 3, H, W) fp16 after the (3,1,1) temporal conv over t"""
+    _dev(x)
+    ld = _rowmajor(x, "x")
+    assert w27.is_contiguous() and w27.numel() == 27 and bias3.numel() == 3
+    out = torch.empty((B * T, 3, H, W), dtype=HALF, device=x.device)
+    L = _L.get_lib()
+    _L.check(L.star_vae_head(_p(x), ld, _p(_h(w27, "w27")), _p(_h(bias3, "bias3")), _p(out), B, T, H * W, _st()),
+             "star_vae_head")
     return out
 
 

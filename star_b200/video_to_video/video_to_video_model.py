@@ -7,10 +7,11 @@ Mirrors ``VideoToVideo_sr`` of the reference's video_to_video/video_to_video_mod
 * the denoiser is star_b200's ``ControlledV2VUNet`` (sm_100a kernels), not autocast PyTorch;
 * the diffusion block of ``test`` (ref :98-123) is factored into ``denoise_latents`` so that
   the latent-in / latent-out hot path can be driven (and benchmarked) without the VAE;
-* the text encoder (open_clip) and the temporal VAE (diffusers) are un-vendored third-party
-  packages: they are imported lazily, and ready-made objects can be injected
-  (``text_encoder=``, ``vae=``, ``generator=``), which is how the tests and the benchmark run
-  on boxes without those packages or checkpoints;
+* the temporal VAE is star_b200's own ``AutoencoderKLTemporalDecoder`` (modules/temporal_vae.py, same
+  checkpoint layout as diffusers', sm_100a kernels), loaded from ``opt.vae_path`` (no hub download);
+* the text encoder (open_clip) is an un-vendored third-party package: it is imported lazily, and
+  ready-made objects can be injected (``text_encoder=``, ``vae=``, ``generator=``), which is how the
+  tests and the benchmark run on boxes without those packages or checkpoints;
 * with ``torch.distributed`` initialised, frame chunks are sharded across ranks
   (diffusion_sdedit.GaussianDiffusion.sample_sr, ``chunk_parallel``).
 """
@@ -57,13 +58,15 @@ class VideoToVideo_sr():
         self.diffusion = GaussianDiffusion(sigmas=sigmas)
 
         if vae is None:
-            try:
-                from diffusers import AutoencoderKLTemporalDecoder
-            except ImportError as e:                                 # pragma: no cover
-                raise ImportError("VideoToVideo_sr needs diffusers' AutoencoderKLTemporalDecoder for pixel I/O; "
-                                  "pass vae=... or use denoise_latents() for the latent-space path") from e
-            vae = AutoencoderKLTemporalDecoder.from_pretrained(
-                "stabilityai/stable-video-diffusion-img2vid", subfolder="vae", variant="fp16")
+            # ref :57-63 downloads stabilityai/stable-video-diffusion-img2vid (subfolder vae, variant fp16) through
+            # diffusers; here the same checkpoint is read from a local snapshot into the sm_100a temporal VAE.
+            from .modules.temporal_vae import AutoencoderKLTemporalDecoder
+            vae_path = getattr(opt, 'vae_path', None) or getattr(cfg, 'vae_path', None)
+            if vae_path is None:
+                raise ValueError("VideoToVideo_sr: pass opt.vae_path (local snapshot of "
+                                 "stabilityai/stable-video-diffusion-img2vid/vae) or vae=...; "
+                                 "denoise_latents() needs neither")
+            vae = AutoencoderKLTemporalDecoder.from_pretrained(vae_path, variant="fp16")
             vae.eval()
             vae.requires_grad_(False)
             vae.to(self.device)

@@ -255,3 +255,73 @@ def test_row_gate_and_qk_ln_rope(env):
     torch.cuda.synchronize()
     R.qk_ln_rope(ref_in, heads, heads * 64, qg, qb, kg, kb, cos, sin, seq, tl, 1e-6)
     assert_close(qkv, ref_in, what="qk_ln_rope")
+
+
+# ---- temporal VAE helpers ---------------------------------------------------------------------------
+@pytest.mark.parametrize("BT,H,W,C,pad", [(2, 16, 24, 128, (0, 1, 0, 1)), (1, 30, 20, 64, (0, 1, 0, 1)),
+                                          (3, 9, 11, 256, (1, 1, 1, 1)), (1, 488, 864, 64, (0, 1, 0, 1))])
+def test_conv2d_s2_padded(env, BT, H, W, C, pad):
+    O, R = env
+    x = rnd(BT, H, W, C, seed=1)
+    w9 = rnd(C, 3, 3, C, seed=2, scale=(9 * C) ** -0.5)
+    bias = rnd(C, seed=3, scale=0.1)
+    got, Ho, Wo = O.conv2d_3x3_s2p(x, w9, bias, pad)
+    torch.cuda.synchronize()
+    ref, Hr, Wr = R.conv2d_3x3_s2p(x, w9, bias, pad)
+    assert (Ho, Wo) == (Hr, Wr)
+    assert_close(got, ref, what=f"conv s2p {BT}x{H}x{W}x{C} pad {pad}")
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(300, 1000, 1000), (77, 26352, 26352), (513, 123, 128), (9, 8, 8)])
+def test_softmax_rows(env, rows, cols, ld):
+    O, R = env
+    s = rnd(rows, ld, seed=4, scale=3.0)
+    ref = R.softmax_rows(s.clone(), cols)
+    got = O.softmax_rows(s, cols)
+    torch.cuda.synchronize()
+    assert torch.equal(got[:, cols:], torch.zeros_like(got[:, cols:]))
+    assert_close(got, ref, what=f"softmax_rows {rows}x{cols}")
+    assert (got.float().sum(dim=1) - 1).abs().max() < 2e-2
+
+
+def test_single_head_attention_as_gemms(env):
+    """the VAE mid-block attention path: S = Q K^T (N = tokens, unaligned), row softmax, P V against V^T"""
+    O, R = env
+    HW, C = 26352 // 8, 512                                       # 3294 tokens: N % 32 != 0 -> direct-store GEMM
+    xn = rnd(HW, C, seed=1)
+    wq, wk, wv = (rnd(C, C, seed=s, scale=C ** -0.5) for s in (2, 3, 4))
+    q, k = O.linear(xn, wq * (C ** -0.5)), O.linear(xn, wk)
+    ld = (HW + 7) // 8 * 8
+    S = torch.empty(HW, ld, device="cuda", dtype=torch.float16)
+    vt = torch.zeros(C, ld, device="cuda", dtype=torch.float16)
+    O.linear(wv, xn, out=vt[:, :HW])
+    O.linear(q, k, out=S[:, :HW])
+    O.softmax_rows(S, HW)
+    o = O.linear(S, vt)
+    torch.cuda.synchronize()
+    qf, kf, vf = q.float(), k.float(), (xn.float() @ wv.float().t())
+    ref = torch.softmax(qf @ kf.t(), dim=-1) @ vf
+    assert_close(vt[:, :HW], vf.t().half(), what="V^T GEMM")
+    assert_close(o, ref, rel=4e-3, what="single-head attention")
+
+
+def test_vae_head_upsample_and_inplace_groupnorm(env):
+    O, R = env
+    B, T, H, W = 2, 3, 10, 12
+    x = rnd(B * T * H * W, 8, seed=1)
+    w27, b3 = rnd(27, seed=2, scale=0.3), rnd(3, seed=3, scale=0.1)
+    assert_close(O.vae_head(x, w27, b3, B, T, H, W), R.vae_head(x, w27, b3, B, T, H, W), what="vae_head")
+    assert_close(O.vae_head(x[: H * W * 2], w27, b3, 1, 2, H, W), R.vae_head(x[: H * W * 2], w27, b3, 1, 2, H, W), what="vae_head T=2")
+    y = rnd(2 * 9 * 4, 128, seed=4)
+    assert torch.equal(O.upsample2x(y, 2, 9, 4), R.upsample2x(y, 2, 9, 4))
+    g = rnd(6 * 50, 128, seed=5)
+    gamma, beta = rnd(128, seed=6), rnd(128, seed=7)
+    ref = R.groupnorm(g, gamma, beta, 6, 1e-6, True)
+    got = O.groupnorm(g, gamma, beta, 6, 1e-6, True, out=g)
+    assert got.data_ptr() == g.data_ptr()
+    assert_close(got, ref, what="in-place groupnorm C=128")
+    rgb = torch.empty(3 * 16 * 24, 8, device="cuda", dtype=torch.float16)
+    xin = rnd(3, 16, 24, 128, seed=8)
+    w9, b = rnd(3, 3, 3, 128, seed=9, scale=(9 * 128) ** -0.5), rnd(3, seed=10, scale=0.1)
+    O.conv2d_3x3(xin, w9, b, out=rgb[:, :3])
+    assert_close(rgb[:, :3], R.conv2d_3x3(xin, w9, b), what="conv 128->3 into ld=8 rows")
