@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="override clip length (default 32, or 16(N+1) for N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace-out", default="", help="write the per-op time table of the timed region to this file")
+    ap.add_argument("--no-vae", action="store_true", help="skip the (separately reported) VAE encode/decode legs")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; not a valid bench line)")
     return ap.parse_args()
 
@@ -245,6 +246,42 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+def time_vae(pipe, latent, F, H, W, dev, ms_per_step):
+    """Temporal VAE around the denoise loop (ref video_to_video_model.py:141-161), synthetic weights: decode of the
+    F-frame clip as 3-frame windows and encode of F frames one by one, device-timed; plus frames/s of the whole
+    50-step pipeline with those legs included."""
+    from star_b200.utils.synth import synth_tensor
+    from star_b200.video_to_video.modules.temporal_vae import AutoencoderKLTemporalDecoder
+    with torch.device("meta"):
+        vae = AutoencoderKLTemporalDecoder()
+    vae.load_state_dict({k: synth_tensor(k, v.shape, 0, dev) for k, v in vae.state_dict().items()}, assign=True)
+    old, pipe.vae = pipe.vae, vae.eval().requires_grad_(False)
+    try:
+        z = latent[:, :, :F].float()
+        pix = torch.rand(1, min(F, 8), 3, 8 * H, 8 * W, device=dev) * 2 - 1          # encode is per frame: time 8, scale to F
+        pipe.vae_decode_chunk(z[:, :, :3], chunk_size=3)
+        pipe.vae_encode(pix[:, :1])
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        vid = pipe.vae_decode_chunk(z, chunk_size=3)
+        ev[1].record()
+        pipe.vae_encode(pix)
+        ev[2].record()
+        torch.cuda.synchronize()
+        dec_ms = ev[0].elapsed_time(ev[1])
+        enc_ms = ev[1].elapsed_time(ev[2]) * F / pix.shape[1]
+        ok = bool(torch.isfinite(vid).all())
+        denoise_s = SCHEDULE_STEPS * ms_per_step / 1e3
+        return {"vae": "star_b200 AutoencoderKLTemporalDecoder (sm_100a kernels), synthetic weights, parity unpinned",
+                "decode_ms_per_frame": dec_ms / F, "encode_ms_per_frame": enc_ms / F, "decoded_finite": ok,
+                "frames_per_s_denoise_only": F / denoise_s,
+                "frames_per_s_denoise_decode": F / (denoise_s + dec_ms / 1e3),
+                "frames_per_s_encode_denoise_decode": F / (denoise_s + (dec_ms + enc_ms) / 1e3)}
+    finally:
+        pipe.vae = old
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -342,6 +379,11 @@ def main():
     d2h = res.numel() * res.element_size()
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- VAE legs (SURVEY 8d ii/iii): decode the clip in 3-frame windows, encode it frame by frame ----
+    vae_info = None
+    if rank == 0 and not args.no_vae:
+        vae_info = time_vae(pipe, out, F, H, W, dev, ms_per_step)
+
     # ---- roofline of the dominant kernel: spatial self-attention at the finest level ------------
     hw0 = H * W
     per_op = {}
@@ -406,12 +448,13 @@ def main():
                        "parallelism": f"chunk-parallel x{world}, per-step x0 all-gather" if world > 1 else "single GPU",
                        "l2": "activations (0.54 GB per tensor) exceed the 126 MB L2; no explicit flush",
                        "step": "one solver step = 2 UNet+ControlNet forwards + guidance + solver update",
-                       "vae": "not timed (un-vendored diffusers module; latent in / latent out)"},
+                       "vae": "timed separately (key `pipeline`); `value` and `e2e` are the latent-in / latent-out "
+                              "denoise loop BASELINE.json's metric is quoted on"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "VideoToVideo_sr.denoise_latents(host tensors, steps=1).cpu() per step"},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "pipeline": vae_info,
             "op_time_share": {k: round(v / sum(per_op.values()), 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
         }
         print(json.dumps(line), flush=True)
