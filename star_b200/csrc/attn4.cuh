@@ -18,6 +18,18 @@
 
 namespace star {
 
+// which of the 64 probability pairs of a row take the FMA-pipe polynomial instead of MUFU.EX2:
+// POLY_EVERY 0 none, 4 -> 1/4, 3 -> 1/3, 2 -> 1/2, 38 -> 3/8 (pairs 2, 5, 7 of every 8)
+template <int POLY_EVERY>
+STAR_DEVINL constexpr bool poly_slot(int e) {
+    if (POLY_EVERY == 38) return (e & 7) == 2 || (e & 7) == 5 || (e & 7) == 7;
+    if (POLY_EVERY <= 0 || POLY_EVERY == 16) return false;
+    return (e % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == POLY_EVERY - 1;
+}
+
+struct TagFalse { static constexpr bool value = false; };
+struct TagTrue { static constexpr bool value = true; };
+
 constexpr int A4_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle (one warpgroup, registers donated); 4-7 / 8-11: softmax
 constexpr int A4_KV_STAGES = 5;
 
@@ -228,9 +240,12 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const float sl2 = p.scale_log2;
             float m_used = 0.f, l_run = 0.f;
 
-            for (int j = 0; j < nt; ++j) {
+            // One KV tile of the online softmax.  TAIL is a compile-time tag: with a run-time `tail` flag ptxas
+            // if-converted the masking into an ISETP + SEL (+ VIADD) per element on EVERY tile -- 386 of the ~1300
+            // instructions per row and tile (SASS count), on warps that are issue-bound.
+            auto kv_tile = [&](const int j, auto tail_tag) {
+                constexpr bool tail = decltype(tail_tag)::value;
                 const int kbase = j * 128;
-                const bool tail = (kbase + 128 > p.Nk);
                 mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
                 uint32_t v[128];
@@ -271,39 +286,42 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 // all exponentials first (registers only), THEN wait for PV(j-1): the ncu capture of the first attn4
                 // showed the softmax groups stalled ~25 % of their time on pv_done with the wait placed before the exps
-                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                // packed fp32x2 arithmetic (FFMA2 / FADD2): the softmax warps are issue-bound, every pair of
+                // probabilities costs one scale-and-shift, one row-sum add and one fp16 pack instead of two each
+                uint64_t l0 = 0ull, l1 = 0ull, l2 = 0ull, l3 = 0ull;
                 uint32_t pk[64];
+                const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(-m_used, -m_used);
 #pragma unroll
                 for (int e = 0; e < 64; ++e) {
                     const int i = e * 2;
-                    const float x0 = fmaf(__uint_as_float(v[i]), sl2, -m_used);
-                    const float x1 = fmaf(__uint_as_float(v[i + 1]), sl2, -m_used);
-                    float p0, p1;
+                    const uint64_t x01 = f2_fma(f2_pack_bits(v[i], v[i + 1]), sl2_2, negm_2);
+                    uint64_t p01;
                     if (POLY_EVERY == 16) {
-                        // packed-half exponentials: ONE MUFU op per two probabilities (the result is the fp16 pair the
-                        // PV MMA consumes anyway; the argument rounding to fp16 perturbs p by <= ~1e-3 relative)
+                        float x0, x1;
+                        f2_unpack(x01, x0, x1);
                         const uint32_t xh = pack_half2(x0, x1);
                         uint32_t ph;
                         asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
-                        pk[e] = ph;
                         const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&ph));
-                        p0 = pf.x;
-                        p1 = pf.y;
-                    } else if (POLY_EVERY > 0 && (e % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == POLY_EVERY - 1) {
-                        p0 = ex2_poly(x0);
-                        p1 = ex2_poly(x1);
-                        pk[e] = pack_half2(p0, p1);
+                        p01 = f2_pack(pf.x, pf.y);
+                    } else if (poly_slot<POLY_EVERY>(e)) {
+                        p01 = ex2_poly2(x01);
                     } else {
-                        p0 = ex2_approx(x0);
-                        p1 = ex2_approx(x1);
-                        pk[e] = pack_half2(p0, p1);
+                        float x0, x1;
+                        f2_unpack(x01, x0, x1);
+                        p01 = f2_pack(ex2_approx(x0), ex2_approx(x1));
                     }
-                    if ((e & 3) == 0) l0 += p0 + p1;
-                    else if ((e & 3) == 1) l1 += p0 + p1;
-                    else if ((e & 3) == 2) l2 += p0 + p1;
-                    else l3 += p0 + p1;
+                    float p0, p1;
+                    f2_unpack(p01, p0, p1);
+                    pk[e] = pack_half2(p0, p1);
+                    if ((e & 3) == 0) l0 = f2_add(l0, p01);
+                    else if ((e & 3) == 1) l1 = f2_add(l1, p01);
+                    else if ((e & 3) == 2) l2 = f2_add(l2, p01);
+                    else l3 = f2_add(l3, p01);
                 }
-                const float l_part = (l0 + l1) + (l2 + l3);
+                float l_lo, l_hi;
+                f2_unpack(f2_add(f2_add(l0, l1), f2_add(l2, l3)), l_lo, l_hi);
+                const float l_part = l_lo + l_hi;
                 if (j > 0) {
                     mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable
                     tc_fence_after();
@@ -327,7 +345,11 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(&p_full[t]);
                 l_run += l_part;
-            }
+            };
+#pragma unroll 1
+            for (int j = 0; j < nt - 1; ++j) kv_tile(j, TagFalse{});
+            if (p.Nk & 127) kv_tile(nt - 1, TagTrue{});
+            else kv_tile(nt - 1, TagFalse{});
             // epilogue: O / l -> fp16
             mbar_wait(&pv_done[t], (nt - 1) & 1);
             tc_fence_after();

@@ -259,4 +259,46 @@ STAR_DEVINL float ex2_poly(float x) {
     p = fmaf(p, f, 0.9999289512634277f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(fr) << 23));
 }
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two lanes' worth of work) ----
+STAR_DEVINL uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+STAR_DEVINL uint64_t f2_pack_bits(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+STAR_DEVINL void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+STAR_DEVINL uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+STAR_DEVINL uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// ex2_poly on a packed pair
+STAR_DEVINL uint64_t ex2_poly2(uint64_t x) {
+    float x0, x1;
+    f2_unpack(x, x0, x1);
+    x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t fr = f2_add(x, f2_pack(12582912.0f, 12582912.0f));
+    const uint64_t t = f2_add(fr, f2_pack(-12582912.0f, -12582912.0f));
+    const uint64_t f = f2_fma(t, f2_pack(-1.0f, -1.0f), x);
+    uint64_t q = f2_fma(f2_pack(0.05508868396282196f, 0.05508868396282196f), f, f2_pack(0.24260404706001282f, 0.24260404706001282f));
+    q = f2_fma(q, f, f2_pack(0.6932762265205383f, 0.6932762265205383f));
+    q = f2_fma(q, f, f2_pack(0.9999289512634277f, 0.9999289512634277f));
+    float q0, q1, r0, r1;
+    f2_unpack(q, q0, q1);
+    f2_unpack(fr, r0, r1);
+    return f2_pack(__int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23)),
+                   __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23)));
+}
 }  // namespace star

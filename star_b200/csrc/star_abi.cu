@@ -292,7 +292,8 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
@@ -491,7 +492,8 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
         switch (g_attn_poly) {
             case 4: attn4_fwd_kernel<4><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
             case 3: attn4_fwd_kernel<3><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 16: attn4_fwd_kernel<16><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 2: attn4_fwd_kernel<2><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
+            case 38: attn4_fwd_kernel<38><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
             default: attn4_fwd_kernel<0><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
         }
         STAR_LAUNCH_CHECK("attn4_fwd");
