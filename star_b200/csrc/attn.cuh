@@ -35,21 +35,33 @@ struct AttnParams {
     int order;              // attn4 MMA issue order: 0 = S,S,PV,PV per KV tile; 1 = S0,PV1,S1,PV0 (anti-phase)
 };
 
-struct AttnSmem {
+// SINGLE = the whole key range is one KV tile (text cross-attention, Nk = 77): no rings, one S / P / O buffer,
+// 256 TMEM columns and 81 KB of shared memory, so that TWO CTAs are resident per SM -- such a CTA is a strictly
+// serial load -> MMA -> softmax -> MMA -> store chain and only co-resident CTAs overlap it (the general
+// configuration holds one CTA per SM: 1.34 ms for the 26 352-token level, 12 % of the HBM rate).
+template <bool SINGLE>
+struct AttnSmemT {
+    static constexpr int STAGES = SINGLE ? 1 : AT_KV_STAGES;
+    static constexpr int NBUF = SINGLE ? 1 : 2;
     static constexpr int Q_BYTES = AT_BQ * AT_D * 2;        // 16 KB
     static constexpr int KV_BYTES = AT_BKV * AT_D * 2;      // 16 KB each
     static constexpr int P_BYTES = AT_BQ * AT_BKV * 2;      // 32 KB
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = OFF_Q + Q_BYTES;
-    static constexpr int OFF_V = OFF_K + AT_KV_STAGES * KV_BYTES;
-    static constexpr int OFF_P = OFF_V + AT_KV_STAGES * KV_BYTES;
-    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+    static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
+    static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;
+    static constexpr int OFF_BAR = OFF_P + NBUF * P_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
+using AttnSmem = AttnSmemT<false>;
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+template <bool SINGLE>
+__global__ void __launch_bounds__(AT_THREADS, SINGLE ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+    using AttnSmem = AttnSmemT<SINGLE>;
+    constexpr int AT_KV_STAGES = AttnSmem::STAGES;           // shadows the namespace constant
+    constexpr uint32_t TMEM_COLS = SINGLE ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::OFF_BAR);
@@ -95,14 +107,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);
+        tmem_alloc<TMEM_COLS>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s0 = tmem_base;            // S[b] at columns b*128
-    const uint32_t tmem_o0 = tmem_base + 256;      // O[b] at columns 256 + b*64
+    const uint32_t tmem_o0 = tmem_base + (SINGLE ? 128 : 256);      // O[b] at columns 256 + b*64 (SINGLE: one O at 128)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -268,7 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 

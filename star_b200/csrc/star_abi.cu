@@ -282,7 +282,8 @@ int star_init(int device) {
     }
     STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<128>::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<160>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmemT<false>::TOTAL));
+    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmemT<true>::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
@@ -524,7 +525,10 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
         return 0;
     }
     dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, batch);
-    attn_fwd_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    if (Nk <= AT_BKV && g_attn_impl != 1)
+        attn_fwd_kernel<true><<<grid, AT_THREADS, AttnSmemT<true>::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    else
+        attn_fwd_kernel<false><<<grid, AT_THREADS, AttnSmemT<false>::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
     STAR_LAUNCH_CHECK("attn_fwd");
     return 0;
 }
