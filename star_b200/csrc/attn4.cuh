@@ -56,7 +56,8 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint64_t* s_free = bars + 13;            // 2   softmax WG t -> MMA : S_t(j) is in registers
     uint64_t* p_full = bars + 15;            // 2   softmax WG t -> MMA : P_t(j) in TMEM, O_t rescaled
     uint64_t* pv_done = bars + 17;           // 2   MMA -> softmax WG t : O_t += P_t(j) V_j retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* turn = bars + 19;              // 2   softmax WG (1-t) -> WG t : "your turn on the MUFU" (exp-phase ping-pong)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,6 +85,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 mbar_init(&s_free[t], 128);
                 mbar_init(&p_full[t], 128);
                 mbar_init(&pv_done[t], 1);
+                mbar_init(&turn[t], 128);
             }
             fence_barrier_init();
         }
@@ -239,6 +241,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t t_p = tmem_base + 384 + t * 64 + lane_off;
             const float sl2 = p.scale_log2;
             float m_used = 0.f, l_run = 0.f;
+            const bool pingpong = (ntq == 2) && p.pingpong != 0;
 
             // One KV tile of the online softmax.  TAIL is a compile-time tag: with a run-time `tail` flag ptxas
             // if-converted the masking into an ISETP + SEL (+ VIADD) per element on EVERY tile -- 386 of the ~1300
@@ -291,6 +294,11 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 uint64_t l0 = 0ull, l1 = 0ull, l2 = 0ull, l3 = 0ull;
                 uint32_t pk[64];
                 const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(-m_used, -m_used);
+                // Exp-phase ping-pong.  Both query tiles start together, so without this the two softmax groups run in
+                // lock-step: both queue on the 16-lane MUFU for ~1500 clk, then both sit in the MUFU-free part of the
+                // iteration (S wait, TMEM load, row max, P store) -- ncu: XU pipe 55 % busy, tensor 36 %.  Taking turns
+                // puts one group's exponentials under the other group's load / max / store phase.
+                if (pingpong) mbar_wait(&turn[t], t == 0 ? ((j & 1) ^ 1) : (j & 1));
 #pragma unroll
                 for (int e = 0; e < 64; ++e) {
                     const int i = e * 2;
@@ -321,6 +329,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 float l_lo, l_hi;
                 f2_unpack(f2_add(f2_add(l0, l1), f2_add(l2, l3)), l_lo, l_hi);
+                if (pingpong) mbar_arrive(&turn[1 - t]);
                 const float l_part = l_lo + l_hi;
                 if (j > 0) {
                     mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable

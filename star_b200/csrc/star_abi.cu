@@ -31,6 +31,7 @@ int g_num_sms = 148;
 int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
 int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
 int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
+int g_attn_pingpong = 1;  // attn4 exp-phase ping-pong between the two softmax groups (debug override STAR_ATTN_PINGPONG)
 int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
 int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
 int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
@@ -306,6 +307,7 @@ int star_init(int device) {
     if (const char* e = getenv("STAR_GEMM_IMPL")) g_gemm_impl = atoi(e);
     if (const char* e = getenv("STAR_ATTN_IMPL")) g_attn_impl = atoi(e);
     if (const char* e = getenv("STAR_ATTN_ORDER")) g_attn_order = atoi(e);
+    if (const char* e = getenv("STAR_ATTN_PINGPONG")) g_attn_pingpong = atoi(e);
     if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
     if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
     if (const char* e = getenv("STAR_ATTN_POLY")) g_attn_poly = atoi(e);
@@ -485,6 +487,7 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
     p.order = g_attn_order;
+    p.pingpong = g_attn_pingpong;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
     const bool multi = Nk > AT_BKV && Nq > AT_BQ;
     if (g_attn_impl == 4 || (g_attn_impl == 0 && multi)) {
