@@ -27,10 +27,19 @@ STAR_DEVINL constexpr bool poly_slot(int e) {
     return (e % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == POLY_EVERY - 1;
 }
 
+STAR_DEVINL void a4_st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+STAR_DEVINL float a4_ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+STAR_DEVINL void a4_named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 struct TagFalse { static constexpr bool value = false; };
 struct TagTrue { static constexpr bool value = true; };
 
 constexpr int A4_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle (one warpgroup, registers donated); 4-7 / 8-11: softmax
+constexpr int A4S_THREADS = 640;     // SPLIT: warps 4-11 query tile 0 (4-7 low score half, 8-11 high half), 12-19 query tile 1
 constexpr int A4_KV_STAGES = 5;
 
 struct Attn4Smem {
@@ -38,12 +47,19 @@ struct Attn4Smem {
     static constexpr int OFF_Q = 0;                           // 2 tiles
     static constexpr int OFF_K = OFF_Q + 2 * TILE;
     static constexpr int OFF_V = OFF_K + A4_KV_STAGES * TILE;
-    static constexpr int OFF_BAR = OFF_V + A4_KV_STAGES * TILE;
+    static constexpr int OFF_X = OFF_V + A4_KV_STAGES * TILE; // SPLIT exchange: float [2 tiles][2 parity][2 halves][128]
+    static constexpr int OFF_BAR = OFF_X + 2 * 2 * 2 * 128 * 4;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <int POLY_EVERY>      // every POLY_EVERY-th exponential uses ex2_poly (0 = never)
-__global__ void __launch_bounds__(A4_THREADS, 1)
+// SPLIT = 1: every query row is handled by TWO softmax threads (score columns [0,64) / [64,128) of the KV tile, O columns
+// [0,32) / [32,64)), 16 softmax warps, 640 threads.  The ncu source view of the SPLIT = 0 kernel shows the two softmax
+// warps of each scheduler busy ~100 % of the time at ~3 clk per instruction (in-order issue, dependent chains) with no
+// pipe saturated (XU 55 %, tensor 36 %, issue 64 %): the limiter is per-warp latency, i.e. too little thread-level
+// parallelism per scheduler; four half-length streams per scheduler attack exactly that.  The halves agree on the row
+// maximum through shared memory and one 256-thread named barrier per KV tile (as attn3.cuh did, but with P in TMEM).
+template <int POLY_EVERY, int SPLIT = 0>      // every POLY_EVERY-th exponential uses ex2_poly (0 = never)
+__global__ void __launch_bounds__(SPLIT ? A4S_THREADS : A4_THREADS, 1)
 attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -82,8 +98,8 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             for (int t = 0; t < 2; ++t) {
                 mbar_init(&s_full[t], 1);
-                mbar_init(&s_free[t], 128);
-                mbar_init(&p_full[t], 128);
+                mbar_init(&s_free[t], SPLIT ? 256 : 128);
+                mbar_init(&p_full[t], SPLIT ? 256 : 128);
                 mbar_init(&pv_done[t], 1);
                 mbar_init(&turn[t], 128);
             }
@@ -228,6 +244,134 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 umma_commit(&pv_done[1]);
                 umma_commit(&kv_empty[j % A4_KV_STAGES]);
             }
+        }
+    } else if constexpr (SPLIT != 0) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int t = (warp - 4) >> 3;                   // query tile
+        const int half = ((warp - 4) >> 2) & 1;          // score columns [64*half, +64) of every KV tile, O columns [32*half, +32)
+        if (t < ntq) {
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;
+            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+            const uint32_t t_s = tmem_base + t * 128 + half * 64 + lane_off;
+            const uint32_t t_o = tmem_base + 256 + t * 64 + half * 32 + lane_off;
+            const uint32_t t_p = tmem_base + 384 + t * 64 + half * 32 + lane_off;     // 64 probabilities = 32 packed columns
+            const uint32_t x_base = smem_u32(smem + Attn4Smem::OFF_X) + (uint32_t)t * 2048u;    // [parity][half][row]
+            const int bar_id = 1 + t;
+            const float sl2 = p.scale_log2;
+            float m_used = 0.f, l_run = 0.f;
+
+            auto kv_tile = [&](const int j, auto tail_tag) {
+                constexpr bool tail = decltype(tail_tag)::value;
+                const int kbase = j * 128 + half * 64;
+                mbar_wait(&s_full[t], j & 1);
+                tc_fence_after();
+                uint32_t v[64];
+                tmem_ld32(t_s, v);
+                tmem_ld32(t_s + 32, v + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_free[t]);
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (kbase + i >= p.Nk) v[i] = 0xff800000u;      // -inf
+                }
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 64; i += 8) {
+                    m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                    m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+                    m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+                    m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+                }
+                const float mx_mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                const uint32_t x_slot = x_base + (uint32_t)(j & 1) * 1024u;
+                a4_st_shared_f32(x_slot + (uint32_t)half * 512u + (uint32_t)r * 4u, mx_mine);
+                a4_named_bar_sync(bar_id, 256);
+                const float mx = fmaxf(mx_mine, a4_ld_shared_f32(x_slot + (uint32_t)(half ^ 1) * 512u + (uint32_t)r * 4u));
+                const float mc = mx * sl2;
+                float factor = 1.f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mc;
+                } else if (mc > m_used + 8.0f) {
+                    factor = ex2_approx(m_used - mc);
+                    m_used = mc;
+                    need = true;
+                }
+                uint64_t l0 = 0ull, l1 = 0ull;
+                uint32_t pk[32];
+                const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(-m_used, -m_used);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int i = e * 2;
+                    const uint64_t x01 = f2_fma(f2_pack_bits(v[i], v[i + 1]), sl2_2, negm_2);
+                    uint64_t p01;
+                    if (poly_slot<POLY_EVERY>(e)) {
+                        p01 = ex2_poly2(x01);
+                    } else {
+                        float x0, x1;
+                        f2_unpack(x01, x0, x1);
+                        p01 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                    }
+                    float p0, p1;
+                    f2_unpack(p01, p0, p1);
+                    pk[e] = pack_half2(p0, p1);
+                    if (e & 1) l1 = f2_add(l1, p01);
+                    else l0 = f2_add(l0, p01);
+                }
+                float l_lo, l_hi;
+                f2_unpack(f2_add(l0, l1), l_lo, l_hi);
+                if (j > 0) {
+                    mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, need)) {
+                        uint32_t o[32];
+                        tmem_ld32(t_o, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        tmem_st32(t_o, o);
+                        tmem_st_wait();
+                        l_run *= factor;
+                    }
+                }
+                tmem_st32(t_p, pk);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[t]);
+                l_run += l_lo + l_hi;
+            };
+#pragma unroll 1
+            for (int j = 0; j < nt - 1; ++j) kv_tile(j, TagFalse{});
+            if (p.Nk & 127) kv_tile(nt - 1, TagTrue{});
+            else kv_tile(nt - 1, TagFalse{});
+            // combine the two halves' row sums, then O / l -> fp16 (each thread stores its 32 output columns)
+            const uint32_t x_slot = x_base + (uint32_t)(nt & 1) * 1024u;
+            a4_st_shared_f32(x_slot + (uint32_t)half * 512u + (uint32_t)r * 4u, l_run);
+            a4_named_bar_sync(bar_id, 256);
+            const float l_tot = l_run + a4_ld_shared_f32(x_slot + (uint32_t)(half ^ 1) * 512u + (uint32_t)r * 4u);
+            mbar_wait(&pv_done[t], (nt - 1) & 1);
+            tc_fence_after();
+            const int q = q0 + t * 128 + r;
+            const float inv = 1.0f / l_tot;
+            uint32_t o[32];
+            tmem_ld32(t_o, o);
+            tmem_ld_wait();
+            if (q < p.Nq) {
+                __half* op = p.out + ((long long)batch * p.Nq + q) * p.ldo + head * 64 + half * 32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 w;
+                    w.x = pack_half2(__uint_as_float(o[u * 8 + 0]) * inv, __uint_as_float(o[u * 8 + 1]) * inv);
+                    w.y = pack_half2(__uint_as_float(o[u * 8 + 2]) * inv, __uint_as_float(o[u * 8 + 3]) * inv);
+                    w.z = pack_half2(__uint_as_float(o[u * 8 + 4]) * inv, __uint_as_float(o[u * 8 + 5]) * inv);
+                    w.w = pack_half2(__uint_as_float(o[u * 8 + 6]) * inv, __uint_as_float(o[u * 8 + 7]) * inv);
+                    reinterpret_cast<uint4*>(op)[u] = w;
+                }
+            }
+            tc_fence_before();
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");

@@ -295,6 +295,8 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
+    STAR_CUDA((cudaFuncSetAttribute(attn4_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL)));
+    STAR_CUDA((cudaFuncSetAttribute(attn4_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL)));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
@@ -490,6 +492,14 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.pingpong = g_attn_pingpong;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
     const bool multi = Nk > AT_BKV && Nq > AT_BQ;
+    if (g_attn_impl == 5) {          // row-split softmax (640 threads)
+        dim3 grid((Nq + 255) / 256, heads, batch);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (g_attn_poly == 0) attn4_fwd_kernel<0, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
+        else attn4_fwd_kernel<4, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
+        STAR_LAUNCH_CHECK("attn4_split_fwd");
+        return 0;
+    }
     if (g_attn_impl == 4 || (g_attn_impl == 0 && multi)) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         cudaStream_t st = (cudaStream_t)stream;
