@@ -109,7 +109,9 @@ def measured_peaks():
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_attn4.txt")
+    path = os.path.join(ROOT, "profiles", "r01_ncu_attn4_split.txt")
+    if not os.path.isfile(path):
+        path = os.path.join(ROOT, "profiles", "r01_ncu_attn4.txt")
     if not os.path.isfile(path):
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -407,7 +409,7 @@ def main():
         flops = 4.0 * hw0 * hw0 * 64 * batch * heads
         avg = sum(t for _, t in attn_ms) / len(attn_ms)
         ach = flops / (avg * 1e-3) / 1e12
-        roof = {"kernel": "attn_fwd_kernel (spatial self-attention, finest level)", "bound": "tensor",
+        roof = {"kernel": "attn4_fwd_kernel<0,1> (spatial self-attention, finest level, row-split softmax)", "bound": "tensor",
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "peak_source": peaks["source"], "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg,
                 "launches_timed": len(attn_ms), "traffic": ncu_traffic_bytes(),

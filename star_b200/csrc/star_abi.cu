@@ -36,6 +36,7 @@ int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
 int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
 int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
 int g_attn_poly = 4;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
+bool g_attn_poly_set = false;   // the row-split kernel defaults to 0 (all MUFU), the thread-per-row kernels to 4
 std::atomic<long long> g_launches{0};
 
 int fail(const char* fmt, ...) {
@@ -312,7 +313,7 @@ int star_init(int device) {
     if (const char* e = getenv("STAR_ATTN_PINGPONG")) g_attn_pingpong = atoi(e);
     if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
     if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
-    if (const char* e = getenv("STAR_ATTN_POLY")) g_attn_poly = atoi(e);
+    if (const char* e = getenv("STAR_ATTN_POLY")) { g_attn_poly = atoi(e); g_attn_poly_set = true; }
     STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TA_WARPS * 2 * TA_MAXT * 128));
     return 0;
@@ -492,15 +493,18 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.pingpong = g_attn_pingpong;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
     const bool multi = Nk > AT_BKV && Nq > AT_BQ;
-    if (g_attn_impl == 5) {          // row-split softmax (640 threads)
+    // Default for the multi-tile case: the row-split kernel with every exponential on the MUFU.  In-step A/B on the full
+    // model (profiles/r01_bench_ab_attention.log): split/poly0 36.3 ms per finest-level launch, split/poly4 38.1,
+    // thread-per-row/poly4 39.2 (all at ~1.70 GHz under the power cap).
+    if (g_attn_impl == 5 || (g_attn_impl == 0 && multi)) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         cudaStream_t st = (cudaStream_t)stream;
-        if (g_attn_poly == 0) attn4_fwd_kernel<0, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
+        if (!g_attn_poly_set || g_attn_poly == 0) attn4_fwd_kernel<0, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
         else attn4_fwd_kernel<4, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
         STAR_LAUNCH_CHECK("attn4_split_fwd");
         return 0;
     }
-    if (g_attn_impl == 4 || (g_attn_impl == 0 && multi)) {
+    if (g_attn_impl == 4) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         cudaStream_t st = (cudaStream_t)stream;
         switch (g_attn_poly) {
