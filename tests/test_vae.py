@@ -151,3 +151,35 @@ def test_encode_gpu(case):
     err = rel_l2(got, ref)
     print(f"temporal VAE encode [{case}] {H}x{W}: rel-L2 vs fp32 oracle {err:.3e}")
     assert got.shape == (2, 8, H // 8, W // 8) and err < 4e-3
+
+
+@pytest.mark.gpu
+def test_pixel_pipeline_gpu():
+    """VideoToVideo_sr.test() end to end on the GPU (row a1): bilinear x upscale + pad_to_fit (720x1280 canvas), VAE
+    encode per frame, chunked 'fast' sampler (14 CFG evaluations) on the reduced UNet, 3-frame-window VAE decode, crop."""
+    from tests.util import SMALL_KW, synth_model
+    from star_b200.video_to_video.utils.seed import setup_seed
+    from star_b200.video_to_video.video_to_video_model import VideoToVideo_sr
+    net, _ = synth_model(SMALL_KW, seed=1, device="cuda")
+    _, _, vae = _setup(SMALL, device="cuda")
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(1, 77, 1024, generator=g).cuda()
+
+    class Text:
+        def __call__(self, s):
+            return emb if s == "a prompt" else -emb
+
+    class Opt:
+        model_path = None
+
+    pipe = VideoToVideo_sr(Opt(), device=torch.device("cuda"), text_encoder=Text(), vae=vae, generator=net)
+    video = torch.rand(4, 3, 64, 96, generator=g) * 2 - 1
+    outs = []
+    for _ in range(2):
+        setup_seed(666)
+        outs.append(pipe.test({"video_data": video, "y": "a prompt", "target_res": (128, 192)}, steps=50, solver_mode="fast",
+                              guide_scale=7.5, max_chunk_len=32))
+    out = outs[0]
+    assert out.shape == (1, 3, 4, 128, 192) and out.dtype == torch.float32 and out.device.type == "cpu"
+    assert torch.isfinite(out).all()
+    assert torch.equal(outs[0], outs[1])            # same seed -> same video (posterior sample, diffuse noise, SDE noise)
