@@ -31,6 +31,7 @@ int g_num_sms = 148;
 int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
 int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
 int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
+int g_gemm_bn256 = 1;     // 128x256 persistent tiles where N % 256 == 0 (debug override STAR_GEMM_BN256=0)
 int g_attn_pingpong = 1;  // attn4 exp-phase ping-pong between the two softmax groups (debug override STAR_ATTN_PINGPONG)
 int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
 int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
@@ -215,7 +216,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     unsigned long long ostr[5], rstr[5];
     strides(d.ldo, ostr);
     if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (d.residual) {
+    if (d.residual && TapGemm2Smem<BN>::RES_TMA) {
         strides(d.ldres, rstr);
         if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
@@ -229,6 +230,8 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     return 0;
 }
 
+inline bool v2_only_small_n(const TapDesc&) { return false; }
+
 int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     const bool geglu = d.flags & TG_GEGLU;
     const bool aligned = (d.N % 32 == 0) && (d.ldo % 8 == 0) && (reinterpret_cast<uintptr_t>(d.out) % 16 == 0) &&
@@ -239,6 +242,11 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     const bool v2_only = d.colscale != nullptr || (d.flags & TG_GELU_TANH);
     if (v2_only && !aligned) return fail("tapgemm: colscale / tanh-GELU epilogues need N %% 32 == 0 and 16-byte aligned rows");
     const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu && !v2_only;
+    // 128x256 tiles (4 x 48 KB stages, two-pass epilogue): 25 % less L2->SM operand traffic per flop and N = 256 MMAs
+    // (137 clk per instruction against a 128 clk floor; N = 128 retires at 73 against 64: profiles/r01_micro_mma_rate.log)
+    const bool wide = aligned && !v2_only_small_n(d) && (d.N % 256 == 0) && !geglu && ((long long)d.ntaps * d.K >= 512) &&
+                      g_gemm_bn256 != 0 && g_gemm_impl != 1;
+    if (wide) return launch_tapgemm2_bn<256>(d, st);
     if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
         if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm2_bn<160>(d, st);
         return launch_tapgemm2_bn<128>(d, st);
@@ -292,6 +300,7 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true))));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
@@ -313,6 +322,7 @@ int star_init(int device) {
     if (const char* e = getenv("STAR_ATTN_PINGPONG")) g_attn_pingpong = atoi(e);
     if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
     if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
+    if (const char* e = getenv("STAR_GEMM_BN256")) g_gemm_bn256 = atoi(e);
     if (const char* e = getenv("STAR_ATTN_POLY")) { g_attn_poly = atoi(e); g_attn_poly_set = true; }
     STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TA_WARPS * 2 * TA_MAXT * 128));

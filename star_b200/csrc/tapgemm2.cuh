@@ -22,14 +22,20 @@ struct TapGemm2Smem {
     static constexpr int A_BYTES = TG_BM * TG_BK * 2;
     static constexpr int B_BYTES = BN * TG_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int OUT_BYTES = TG_BM * BN * 2;                  // BN/32 sub-tiles of [128 rows x 64 B]
+    // BN = 256 (48 KB stages): the staging buffer holds 128 output columns and the epilogue makes two passes over it,
+    // and the residual is read straight from global memory -- that leaves room for 4 operand stages.
+    static constexpr int OUT_COLS = BN > 160 ? 128 : BN;
+    static constexpr bool RES_TMA = BN <= 160;
+    static constexpr int OUT_BYTES = TG_BM * OUT_COLS * 2;            // OUT_COLS/32 sub-tiles of [128 rows x 64 B]
     static constexpr int BUDGET = 232448 - 1024 - 256;                // 227 KB minus alignment slack and barriers
     // as many operand stages as fit beside the staging buffer (and the residual buffer when there is one)
     static constexpr int stages(bool has_res) {
-        int n = (BUDGET - OUT_BYTES * (has_res ? 2 : 1)) / STAGE_BYTES;
+        int n = (BUDGET - OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1)) / STAGE_BYTES;
         return n > TG2_MAX_STAGES ? TG2_MAX_STAGES : n;
     }
-    static constexpr int total(bool has_res) { return stages(has_res) * STAGE_BYTES + OUT_BYTES * (has_res ? 2 : 1) + 256 + 1024; }
+    static constexpr int total(bool has_res) {
+        return stages(has_res) * STAGE_BYTES + OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1) + 256 + 1024;
+    }
 };
 
 STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
@@ -61,7 +67,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int NS = ex.stages;
     const int OFF_OUT = NS * SM::STAGE_BYTES;
     const int OFF_RES = OFF_OUT + SM::OUT_BYTES;
-    const int OFF_BAR = OFF_OUT + SM::OUT_BYTES * (p.residual ? 2 : 1);
+    const bool res_tma = SM::RES_TMA && p.residual != nullptr;         // residual tile prefetched by TMA (else: direct loads)
+    const int OFF_BAR = OFF_OUT + SM::OUT_BYTES * (res_tma ? 2 : 1);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + TG2_MAX_STAGES;
     uint64_t* acc_full = empty_bar + TG2_MAX_STAGES; // 2
@@ -143,7 +150,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (++s == NS) { s = 0; ph ^= 1; }
                     }
                 }
-                if (has_res) {
+                if (res_tma) {
                     // residual tile of THIS output tile, issued after its operand loads so that waiting for the
                     // previous epilogue to release the buffer never delays the operand prefetch
                     const int n_base = n_tile * n_per_tile;
@@ -205,9 +212,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tile_origin(tile, org, n_tile);
             const int buf = local & 1;
             const int n_base = n_tile * n_per_tile;
-            // time-embedding row of this tile row (unet_v2v.py:684); rows of one tile may belong to different clips
+            // global output row of this tile row (clamped to the tensor for clipped rows): time-embedding row
+            // (unet_v2v.py:684; rows of one tile may belong to different clips) and direct residual loads
             const __half* rv_row = nullptr;
-            if (p.rowvec) {
+            const __half* res_g = nullptr;
+            if (p.rowvec || (has_res && !res_tma)) {
                 int rr = r;
                 long long orow = 0, mul = 1;
 #pragma unroll
@@ -219,18 +228,23 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     orow += (long long)g * mul;
                     mul *= p.on[i];
                 }
-                rv_row = p.rowvec + (orow / p.rowvec_div) * (long long)p.N;
+                if (p.rowvec) rv_row = p.rowvec + (orow / p.rowvec_div) * (long long)p.N;
+                if (has_res && !res_tma) res_g = p.residual + orow * p.res_ld;
             }
             mbar_wait(&acc_full[buf], (local >> 1) & 1);
             tc_fence_after();
-            if (has_res) mbar_wait(res_full, local & 1);
-            // previous tile's TMA stores must have finished reading the staging buffer
-            if (leader) tma_store_wait_read();
-            epi_bar_sync();
+            if (res_tma) mbar_wait(res_full, local & 1);
             const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
             const int last_c0 = ((n_per_tile / 32 - 1 - ehalf) & ~1) * 32 + ehalf * 32;   // last chunk of this warp
+            constexpr int PASS_COLS = SM::OUT_COLS;
 #pragma unroll 1
-            for (int c0 = ehalf * 32; c0 < n_per_tile; c0 += 64) {
+            for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS) {
+            // the TMA stores of the previous pass / tile must have finished reading the staging buffer
+            if (leader) tma_store_wait_read();
+            epi_bar_sync();
+            const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
+#pragma unroll 1
+            for (int c0 = pass0 + ehalf * 32; c0 < pass_end; c0 += 64) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(t_row + c0, v);
@@ -295,14 +309,24 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                     }
                 }
-                const int sub = c0 >> 5;
-                if (has_res) {
+                const int sub = (c0 - pass0) >> 5;
+                if (res_tma) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float rv[8];
                         unpack8h(*reinterpret_cast<const uint4*>(res_row + sub * 8192 + ((u ^ swz) * 16)), rv);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[u * 8 + e] += rv[e];
+                    }
+                } else if (res_g) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (n0 + u * 8 + 8 <= p.N) {
+                            float rv[8];
+                            unpack8h(__ldg(reinterpret_cast<const uint4*>(res_g + n0 + u * 8)), rv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[u * 8 + e] += rv[e];
+                        }
                     }
                 }
                 if (p.flags & TG_SILU_OUT) {
@@ -319,16 +343,17 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     *reinterpret_cast<uint4*>(out_row + sub * 8192 + ((u ^ swz) * 16)) = o;
                 }
             }
-            if (has_res) mbar_arrive(res_empty);
+            if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
             fence_proxy_async_smem();
             epi_bar_sync();
             if (leader) {
 #pragma unroll 1
-                for (int sb = 0; sb < n_per_tile / 32; ++sb) {
-                    if (n_base + sb * 32 < p.N)
-                        tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + sb * 32, org[0], org[1], org[2], org[3]);
+                for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
+                    if (n_base + pass0 + sb * 32 < p.N)
+                        tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
                 }
                 tma_store_commit();
+            }
             }
         }
         if (leader) tma_store_wait_all();

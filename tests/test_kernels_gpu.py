@@ -36,6 +36,10 @@ def rnd(*shape, seed=0, scale=1.0):
     (640, 512, 2048, 1, "bias"),
     (900, 640, 640, 0, "bias,res,rowvec"),
     (1500, 2560, 320, 0, "bias"),
+    (3000, 640, 1280, 0, "bias,res,rowvec"),      # N % 256 == 0: 128x256 tiles, two-pass epilogue, direct residual loads
+    (129, 2560, 256, 0, "bias"),
+    (5000, 512, 1536, 0, ""),
+    (777, 1280, 3840, 2, "bias,res"),
 ])
 def test_linear(env, rows, K, N, flags, extras):
     O, R = env
@@ -69,6 +73,8 @@ def test_linear_strided_views(env):
     (2, 17, 27, 320, 4, "bias"),
     (4, 3, 2, 1280, 1280, "bias,res"),
     (2, 34, 32, 960, 320, "bias,rowvec,res"),
+    (2, 17, 27, 1280, 1280, "bias,rowvec,res"),
+    (3, 33, 20, 128, 256, "bias,res"),
 ])
 def test_conv2d_3x3(env, BT, H, W, Cin, Cout, extras):
     O, R = env
