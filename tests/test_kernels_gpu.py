@@ -40,6 +40,9 @@ def rnd(*shape, seed=0, scale=1.0):
     (129, 2560, 256, 0, "bias"),
     (5000, 512, 1536, 0, ""),
     (777, 1280, 3840, 2, "bias,res"),
+    (1111, 640, 2560, 1, "bias"),                 # GEGLU on 128x256 tiles (128 outputs per tile)
+    (600, 1280, 1920, 0, "bias"),                 # padded width 2048
+    (900, 640, 960, 0, "bias,res"),
 ])
 def test_linear(env, rows, K, N, flags, extras):
     O, R = env
