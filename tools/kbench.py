@@ -82,6 +82,15 @@ def bench_linear():
     R = F * H * W
     a, w, bias = rnd(R, C), rnd(3 * C, C, scale=C ** -0.5), None
     report("linear L2 qkv (1280->3840)", timeit(lambda: O.linear(a, w)), flops=2.0 * R * C * 3 * C)
+    H, W, C = LEVELS[1]
+    R = F * H * W
+    a = rnd(R, C)
+    for (N, res, name) in [(C, True, "to_out (640->640,+res)"), (3 * C, False, "qkv (640->1920)")]:
+        w, r = rnd(N, C, scale=C ** -0.5), (rnd(R, N) if res else None)
+        report(f"linear L1 {name}", timeit(lambda: O.linear(a, w, None, r)), flops=2.0 * R * C * N)
+    a4, w4, r4 = rnd(R, 4 * C), rnd(C, 4 * C, scale=(4 * C) ** -0.5), rnd(R, C)
+    report("linear L1 FF out (2560->640,+res)", timeit(lambda: O.linear(a4, w4, None, r4)), flops=2.0 * R * 4 * C * C)
+    del a4, w4, r4
     for lvl in (1, 2):
         H, W, C = LEVELS[lvl]
         R = F * H * W
