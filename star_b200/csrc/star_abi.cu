@@ -31,6 +31,7 @@ int g_num_sms = 148;
 int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
 int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
 int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
+int g_gemm_wide_waste_longk = 25;   // ... and for reductions >= 1920 (N = 640 as 3 x 256: +16 % on the 640-channel convs)
 int g_gemm_wide_waste = 10;   // largest padding (percent of N) accepted for the 128x256 tiles (STAR_GEMM_WIDE_WASTE)
 int g_gemm_wide_mink = 256;   // smallest reduction length that takes the 128x256 tiles (STAR_GEMM_WIDE_MINK)
 int g_gemm_bn256 = 1;     // 128x256 persistent tiles where N % 256 == 0 (debug override STAR_GEMM_BN256=0)
@@ -244,10 +245,11 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu && !v2_only;
     // 128x256 tiles (4 x 48 KB stages, two-pass epilogue): 25 % less L2->SM operand traffic per flop and N = 256 MMAs
     // (137 clk per instruction against a 128 clk floor; N = 128 retires at 73 against 64: profiles/r01_micro_mma_rate.log)
-    // Used when the padded width wastes <= 10 % (N = 960, 1280, 1920, 2560, 3840, ...; GEGLU: 128 outputs per tile).
+    // Used when the padded width wastes <= 10 % (<= 25 % for long reductions, where the tile-shape gain outweighs it:
+    // profiles/r01_kbench_wide_tiles.log) (N = 960, 1280, 1920, 2560, 3840, ...; GEGLU: 128 outputs per tile).
     const int wide_n = geglu ? 128 : 256;
     const long long padded = ((long long)d.N + wide_n - 1) / wide_n * wide_n;
-    const bool wide = aligned && (padded * 100 <= (long long)d.N * (100 + g_gemm_wide_waste)) && ((long long)d.ntaps * d.K >= g_gemm_wide_mink) &&
+    const bool wide = aligned && (padded * 100 <= (long long)d.N * (100 + ((long long)d.ntaps * d.K >= 1920 ? g_gemm_wide_waste_longk : g_gemm_wide_waste))) && ((long long)d.ntaps * d.K >= g_gemm_wide_mink) &&
                       g_gemm_bn256 != 0 && !(geglu && g_gemm_bn256 == 2) && g_gemm_impl != 1;
     if (wide) return launch_tapgemm2_bn<256>(d, st);
     if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
