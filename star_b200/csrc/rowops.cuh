@@ -219,6 +219,149 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
     for (; i < n; i += stride) apply(i, __ldg(reinterpret_cast<const uint4*>(x) + i));
 }
 
+// ---- second generation (default): persistent CTAs over CONTIGUOUS runs of 128-row slabs -------------------------
+// gn_stats / gn_apply above ran at 48 % of the copy bandwidth (kbench): a CTA lived for one 160 KB slab (launch +
+// block reduction + atomics per slab), and gn_apply re-read its 16 (a, b) pairs (64 B from L1) for every 16 B of
+// activations -- 115 B/clk/SM of L1 traffic at the HBM rate, i.e. L1-bound.  Here a CTA walks a contiguous range of
+// slabs (slab = GN2_SLAB rows of ONE sample, so a range crosses a sample boundary rarely): statistics stay in
+// registers until the sample changes, and the per-channel (a, b) live in registers and are reloaded only then.
+constexpr int GN2_SLAB = 128;
+constexpr int GN2_THREADS = 256;
+
+struct Gn2Range {
+    long long slabs_per_sample, total_slabs;
+    __device__ void span(long long& g0, long long& g1) const {      // contiguous, balanced to +-1 slab
+        const long long per = total_slabs / gridDim.x, extra = total_slabs % gridDim.x;
+        g0 = per * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
+        g1 = g0 + per + (blockIdx.x < extra ? 1 : 0);
+    }
+};
+
+__global__ void __launch_bounds__(GN2_THREADS)
+gn_stats2_kernel(const __half* __restrict__ x, double* __restrict__ stats, long long rows_per_sample, int C, Gn2Range rg) {
+    extern __shared__ float red[];            // [lanes][C][2]
+    const int O = C / 8;                      // host guarantees O <= GN2_THREADS
+    const int lanes = GN2_THREADS / O;
+    const int tid = threadIdx.x;
+    const int oc = tid % O, ln = tid / O;
+    const bool active = ln < lanes;
+    const int cg = C / 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    long long g0, g1;
+    rg.span(g0, g1);
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    long long cur = g0 < g1 ? g0 / rg.slabs_per_sample : -1;
+    auto flush = [&](long long sample) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[((size_t)ln * C + oc * 8 + j) * 2] = s[j];
+                red[((size_t)ln * C + oc * 8 + j) * 2 + 1] = ss[j];
+                s[j] = ss[j] = 0.f;
+            }
+        }
+        __syncthreads();
+        for (int g = warp; g < 32; g += GN2_THREADS / 32) {
+            float a = 0.f, b = 0.f;
+            for (int i = lane; i < lanes * cg; i += 32) {
+                const int l2 = i / cg, c = g * cg + i % cg;
+                a += red[((size_t)l2 * C + c) * 2];
+                b += red[((size_t)l2 * C + c) * 2 + 1];
+            }
+            a = warp_sum(a);
+            b = warp_sum(b);
+            if (lane == 0) {
+                atomicAdd(&stats[(sample * 32 + g) * 2], (double)a);
+                atomicAdd(&stats[(sample * 32 + g) * 2 + 1], (double)b);
+            }
+        }
+        __syncthreads();
+    };
+    for (long long g = g0; g < g1; ++g) {
+        const long long sample = g / rg.slabs_per_sample;
+        if (sample != cur) {                  // uniform across the CTA
+            flush(cur);
+            cur = sample;
+        }
+        const long long r0 = (g - sample * rg.slabs_per_sample) * GN2_SLAB;
+        const long long r1 = min(rows_per_sample, r0 + GN2_SLAB);
+        if (active) {
+            const __half* xs = x + (sample * rows_per_sample) * C + oc * 8;
+            long long r = r0 + ln;
+            for (; r + 3ll * lanes < r1; r += 4ll * lanes) {          // 4 independent 16-byte loads in flight
+                uint4 u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + (long long)k * lanes) * C));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float f[8];
+                    unpack8(u[k], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+                }
+            }
+            for (; r < r1; r += lanes) {
+                float f[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(xs + r * C)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+            }
+        }
+    }
+    if (cur >= 0) flush(cur);
+}
+
+__global__ void __launch_bounds__(GN2_THREADS)
+gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ out,
+                 long long rows_per_sample, int C, int silu, Gn2Range rg) {
+    const int O = C / 8;
+    const int lanes = GN2_THREADS / O;
+    const int tid = threadIdx.x;
+    const int oc = tid % O, ln = tid / O;
+    if (ln >= lanes) return;
+    long long g0, g1;
+    rg.span(g0, g1);
+    float a[8], b[8];
+    long long cur = -1;
+    auto apply = [&](const uint4& raw, __half* dst) {
+        float f[8];
+        unpack8(raw, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(f[j], a[j], b[j]);
+            if (silu) y = silu_f(y);
+            f[j] = y;
+        }
+        *reinterpret_cast<uint4*>(dst) = pack8(f);
+    };
+    for (long long g = g0; g < g1; ++g) {
+        const long long sample = g / rg.slabs_per_sample;
+        if (sample != cur) {
+            cur = sample;
+            const float4* abp = reinterpret_cast<const float4*>(ab + (sample * C + oc * 8) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 q = __ldg(abp + j);
+                a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
+            }
+        }
+        const long long r0 = (g - sample * rg.slabs_per_sample) * GN2_SLAB;
+        const long long r1 = min(rows_per_sample, r0 + GN2_SLAB);
+        const long long base = (sample * rows_per_sample) * C + oc * 8;
+        long long r = r0 + ln;
+        for (; r + 3ll * lanes < r1; r += 4ll * lanes) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (r + (long long)k * lanes) * C));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) apply(u[k], out + base + (r + (long long)k * lanes) * C);
+        }
+        for (; r < r1; r += lanes) apply(__ldg(reinterpret_cast<const uint4*>(x + base + r * C)), out + base + r * C);
+    }
+}
+
 // ------------------------------------------------------------------ LayerNorm over C with fused LIEM gate
 // gate_mode 0: y = LN(x)
 // gate_mode 1: y = LN(x * gate[row])            spatial LIEM, gate from liem_spatial_gate (unet_v2v.py:468-473)
@@ -304,6 +447,105 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
         for (int i = 0; i < LN_OCT; ++i) {
             const int oc = lane + 32 * i;
             if (oc < O) {
+                float gm[8], bt[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + oc * 8)), gm);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(beta + oc * 8)), bt);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+                *reinterpret_cast<uint4*>(out + row * C + oc * 8) = pack8(v[i]);
+            }
+        }
+    }
+}
+
+// Narrow rows: C = 40 * LPR channels (320 -> LPR 8, 640 -> LPR 16).  A warp normalises 32 / LPR rows at once, LPR lanes
+// x 5 sixteen-byte groups per row, every lane busy (layernorm_kernel<2> keeps only 20 of 32 lanes busy at C = 320 and
+// spends a full 5-step shuffle tree per row: ~150 instructions per row against ~80 here; see
+// profiles/r01_kbench_rowops_v2.log).  Same arithmetic and gate modes as layernorm_kernel.
+template <int LPR>
+__global__ void __launch_bounds__(256, 2)
+layernorm_sub_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                     __half* __restrict__ out, long long rows, float eps, int gate_mode, const __half* __restrict__ gate,
+                     float w0, float w1) {
+    constexpr int RPW = 32 / LPR;             // rows per warp and iteration
+    constexpr int C = 40 * LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long ngroups = (rows + RPW - 1) / RPW;
+    long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (grp >= ngroups) return;
+    const float inv_c = 1.0f / (float)C;
+    auto sub_sum = [](float v) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    auto sub_max = [](float v) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    };
+    uint4 nxt[5];
+    {
+        const long long row = grp * RPW + sub;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            nxt[i] = row < rows ? __ldg(reinterpret_cast<const uint4*>(x + row * C + (sl + LPR * i) * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    for (; grp < ngroups; grp += nwarps) {
+        const long long row = grp * RPW + sub;
+        const bool valid = row < rows;
+        float v[5][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            unpack8(nxt[i], v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        }
+        const long long nrow = (grp + nwarps) * RPW + sub;
+        if (grp + nwarps < ngroups) {                   // prefetch this lane's share of the warp's next row group
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                nxt[i] = nrow < rows ? __ldg(reinterpret_cast<const uint4*>(x + nrow * C + (sl + LPR * i) * 8)) : make_uint4(0, 0, 0, 0);
+        }
+        if (gate_mode != 0) {
+            float g;
+            if (gate_mode == 1) {
+                g = valid ? __half2float(gate[row]) : 0.f;
+            } else {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[i][j]);
+                s = sub_sum(s);
+                mx = sub_max(mx);
+                const float mean_h = __half2float(__float2half_rn(s * inv_c));
+                const float lin = __half2float(__float2half_rn(w0 * mx + w1 * mean_h));
+                g = __half2float(__float2half_rn(sigmoid_f(lin)));
+            }
+            s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[i][j] = __half2float(__float2half_rn(v[i][j] * g));     // fp16 product, as the reference
+                    s += v[i][j];
+                }
+        }
+        const float mean = sub_sum(s) * inv_c;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var = fmaf(d, d, var); }
+        const float rstd = rsqrtf(sub_sum(var) * inv_c + eps);
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int oc = sl + LPR * i;
                 float gm[8], bt[8];
                 unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + oc * 8)), gm);
                 unpack8(__ldg(reinterpret_cast<const uint4*>(beta + oc * 8)), bt);

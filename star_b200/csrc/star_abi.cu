@@ -34,6 +34,8 @@ int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override
 int g_gemm_wide_waste_longk = 25;   // ... and for reductions >= 1920 (N = 640 as 3 x 256: +16 % on the 640-channel convs)
 int g_gemm_wide_waste = 10;   // largest padding (percent of N) accepted for the 128x256 tiles (STAR_GEMM_WIDE_WASTE)
 int g_gemm_wide_mink = 256;   // smallest reduction length that takes the 128x256 tiles (STAR_GEMM_WIDE_MINK)
+int g_ln_impl = 0;         // 1 = one-row-per-warp LayerNorm for every width (debug override STAR_LN_IMPL)
+int g_gn_impl = 0;         // 1 = first-generation GroupNorm kernels (debug override STAR_GN_IMPL)
 int g_gemm_bn256 = 1;     // 128x256 persistent tiles where N % 256 == 0 (debug override STAR_GEMM_BN256=0)
 int g_attn_pingpong = 1;  // attn4 exp-phase ping-pong between the two softmax groups (debug override STAR_ATTN_PINGPONG)
 int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
@@ -328,6 +330,8 @@ int star_init(int device) {
     if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
     if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
     if (const char* e = getenv("STAR_GEMM_BN256")) g_gemm_bn256 = atoi(e);
+    if (const char* e = getenv("STAR_GN_IMPL")) g_gn_impl = atoi(e);
+    if (const char* e = getenv("STAR_LN_IMPL")) g_ln_impl = atoi(e);
     if (const char* e = getenv("STAR_GEMM_WIDE_MINK")) g_gemm_wide_mink = atoi(e);
     if (const char* e = getenv("STAR_GEMM_WIDE_WASTE")) g_gemm_wide_waste = atoi(e);
     if (const char* e = getenv("STAR_ATTN_POLY")) { g_attn_poly = atoi(e); g_attn_poly_set = true; }
@@ -609,6 +613,23 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
     double* stats = (double*)workspace;
     float* ab = (float*)((char*)workspace + (size_t)nsamples * 32 * 2 * 8);
     STAR_CUDA(cudaMemsetAsync(stats, 0, (size_t)nsamples * 32 * 2 * 8, st));
+    const long long total_rows = rows_per_sample * nsamples;
+    if (C / 8 <= GN2_THREADS && g_gn_impl != 1) {
+        // persistent CTAs over contiguous slab ranges: statistics / (a, b) stay in registers across slabs
+        Gn2Range rg;
+        rg.slabs_per_sample = (rows_per_sample + GN2_SLAB - 1) / GN2_SLAB;
+        rg.total_slabs = rg.slabs_per_sample * nsamples;
+        const int lanes2 = GN2_THREADS / (C / 8);
+        const size_t smem2 = (size_t)lanes2 * C * 2 * sizeof(float);
+        const unsigned grid2 = (unsigned)std::min<long long>(rg.total_slabs, (long long)g_num_sms * 8);
+        gn_stats2_kernel<<<grid2, GN2_THREADS, smem2, st>>>((const __half*)X, stats, rows_per_sample, C, rg);
+        STAR_LAUNCH_CHECK("gn_stats2");
+        gn_finalize_kernel<<<nsamples, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows_per_sample, C, eps);
+        STAR_LAUNCH_CHECK("gn_finalize");
+        gn_apply2_kernel<<<grid2, GN2_THREADS, 0, st>>>((const __half*)X, ab, (__half*)out, rows_per_sample, C, silu, rg);
+        STAR_LAUNCH_CHECK("gn_apply2");
+        return 0;
+    }
     const int lanes = std::max(1, GN_THREADS / (C / 8));
     const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
     dim3 grid((unsigned)((rows_per_sample + GN_SLAB - 1) / GN_SLAB), nsamples);
@@ -616,7 +637,6 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
     STAR_LAUNCH_CHECK("gn_stats");
     gn_finalize_kernel<<<nsamples, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows_per_sample, C, eps);
     STAR_LAUNCH_CHECK("gn_finalize");
-    const long long total_rows = rows_per_sample * nsamples;
     gn_apply_kernel<<<grid_for(total_rows * (C / 8), 256), 256, 0, st>>>((const __half*)X, ab, (__half*)out, rows_per_sample,
                                                                           total_rows, C, silu);
     STAR_LAUNCH_CHECK("gn_apply");
@@ -626,6 +646,19 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
 int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,
                    int gate_mode, const void* gate, float w0, float w1, void* stream) {
     if (C % 8 || C / 8 > 32 * 12) return fail("star_layernorm: unsupported C=%d", C);
+    if ((C == 320 || C == 640) && g_ln_impl != 1) {
+        const int rpw = C == 320 ? 4 : 2;
+        const long long groups = (rows + rpw - 1) / rpw;
+        const unsigned g2 = (unsigned)std::min<long long>((groups + 7) / 8, (long long)g_num_sms * 6);
+        if (C == 320)
+            layernorm_sub_kernel<8><<<g2, 256, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma, (const __half*)beta,
+                                                                          (__half*)out, rows, eps, gate_mode, (const __half*)gate, w0, w1);
+        else
+            layernorm_sub_kernel<16><<<g2, 256, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma, (const __half*)beta,
+                                                                           (__half*)out, rows, eps, gate_mode, (const __half*)gate, w0, w1);
+        STAR_LAUNCH_CHECK("layernorm_sub");
+        return 0;
+    }
     const int wpb = 8;
     const long long want = (rows + wpb - 1) / wpb;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 6);

@@ -174,7 +174,8 @@ def test_temporal_attention(env, B, T, HW, heads, Ci):
 
 
 @pytest.mark.parametrize("ns,rps,C,silu", [(8, 288, 320, 1), (1, 8 * 288, 320, 1), (3, 100, 2560, 0), (2, 459, 1280, 1),
-                                           (4, 77, 960, 1), (1, 26352, 640, 0)])
+                                           (4, 77, 960, 1), (1, 26352, 640, 0), (32, 26352, 320, 1), (5, 129, 1920, 1),
+                                           (3, 1, 128, 0), (7, 300, 64, 1)])
 def test_groupnorm(env, ns, rps, C, silu):
     O, R = env
     x = rnd(ns * rps, C, seed=1) + 0.5
@@ -186,7 +187,8 @@ def test_groupnorm(env, ns, rps, C, silu):
     assert_close(got, R.groupnorm(x, gamma, beta, ns, eps, silu), what=f"groupnorm {ns},{rps},{C}")
 
 
-@pytest.mark.parametrize("rows,C,mode", [(1000, 320, 0), (999, 512, 2), (300, 1280, 1), (64, 640, 2), (5, 320, 1)])
+@pytest.mark.parametrize("rows,C,mode", [(1000, 320, 0), (999, 512, 2), (300, 1280, 1), (64, 640, 2), (5, 320, 1), (1001, 320, 2),
+                                         (3, 640, 0), (4097, 640, 1), (26353, 320, 1)])
 def test_layernorm(env, rows, C, mode):
     O, R = env
     x = rnd(rows, C, seed=1)
