@@ -237,25 +237,22 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
             const int last_c0 = ((n_per_tile / 32 - 1 - ehalf) & ~1) * 32 + ehalf * 32;   // last chunk of this warp
             constexpr int PASS_COLS = SM::OUT_COLS;
-            uint32_t vA[32], vB[32];
-            bool use_a = true, preloaded = false;
 #pragma unroll 1
             for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS) {
             // the TMA stores of the previous pass / tile must have finished reading the staging buffer
             if (leader) tma_store_wait_read();
             epi_bar_sync();
             const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
-            // One 32-column chunk.  Its TMEM load was issued earlier; the load of the warp's NEXT chunk (possibly the first
-            // one of the next pass) is issued as soon as this one has landed, so its ~300 clk latency runs under the bias /
-            // activation / pack work instead of in front of it (short-K tiles are epilogue-latency bound).
-            auto chunk = [&](uint32_t (&v)[32], const int c0, uint32_t (&vnext)[32], const int cnext) {
+#pragma unroll 1
+            for (int c0 = pass0 + ehalf * 32; c0 < pass_end; c0 += 64) {
+                uint32_t v[32];
                 float f[32];
+                tmem_ld32(t_row + c0, v);
                 const int n0 = n_base + c0;
                 if (geglu) {
                     uint32_t g[32];
                     tmem_ld32(t_row + (BN / 2) + c0, g);
                     tmem_ld_wait();
-                    if (cnext >= 0) tmem_ld32(t_row + cnext, vnext);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float bv[8], bg[8];
@@ -273,7 +270,6 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     }
                 } else {
                     tmem_ld_wait();
-                    if (cnext >= 0) tmem_ld32(t_row + cnext, vnext);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float bv[8];
@@ -345,24 +341,6 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     o.z = pack_half2(f[u * 8 + 4], f[u * 8 + 5]);
                     o.w = pack_half2(f[u * 8 + 6], f[u * 8 + 7]);
                     *reinterpret_cast<uint4*>(out_row + sub * 8192 + ((u ^ swz) * 16)) = o;
-                }
-            };
-            {
-                int c0 = pass0 + ehalf * 32;
-                if (!preloaded && c0 < pass_end) {
-                    tmem_ld32(t_row + c0, vA);
-                    use_a = true;
-                }
-                preloaded = false;
-#pragma unroll 1
-                for (; c0 < pass_end; c0 += 64) {
-                    int nxt = c0 + 64;
-                    if (nxt >= pass_end) nxt = (pass_end < n_per_tile) ? pass_end + ehalf * 32 : -1;
-                    if (nxt >= n_per_tile) nxt = -1;
-                    if (use_a) chunk(vA, c0, vB, nxt);
-                    else chunk(vB, c0, vA, nxt);
-                    use_a = !use_a;
-                    preloaded = nxt >= pass_end;          // the next pass's first chunk is already on its way
                 }
             }
             if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
