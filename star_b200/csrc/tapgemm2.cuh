@@ -22,22 +22,19 @@ struct TapGemm2Smem {
     static constexpr int A_BYTES = TG_BM * TG_BK * 2;
     static constexpr int B_BYTES = BN * TG_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // Output staging: the two epilogue groups (warps 4-7 / 8-11, alternate 32-column chunks) each own two 8 KB sub-tile
-    // buffers [128 rows x 64 B] and stream them out with one TMA store per chunk (one store may still be draining while
-    // the next chunk is computed).  The first version staged a whole pass behind a 256-thread barrier and waited for the
-    // stores to drain before the next pass: on short-K tiles the epilogue warps spent 3.5 stall cycles per issue at that
-    // barrier (profiles/r01_ncu_gemm256_l0.txt).
-    static constexpr int OUT_BYTES = 4 * 8192;
-    static constexpr bool RES_TMA = BN <= 160;                         // BN = 256: residual read straight from global
-    static constexpr int RES_BYTES = RES_TMA ? TG_BM * BN * 2 : 0;     // BN/32 sub-tiles of [128 rows x 64 B]
+    // BN = 256 (48 KB stages): the staging buffer holds 128 output columns and the epilogue makes two passes over it,
+    // and the residual is read straight from global memory -- that leaves room for 4 operand stages.
+    static constexpr int OUT_COLS = BN > 160 ? 128 : BN;
+    static constexpr bool RES_TMA = BN <= 160;
+    static constexpr int OUT_BYTES = TG_BM * OUT_COLS * 2;            // OUT_COLS/32 sub-tiles of [128 rows x 64 B]
     static constexpr int BUDGET = 232448 - 1024 - 256;                // 227 KB minus alignment slack and barriers
-    // as many operand stages as fit beside the staging buffers (and the residual buffer when there is one)
+    // as many operand stages as fit beside the staging buffer (and the residual buffer when there is one)
     static constexpr int stages(bool has_res) {
-        int n = (BUDGET - OUT_BYTES - ((has_res && RES_TMA) ? RES_BYTES : 0)) / STAGE_BYTES;
+        int n = (BUDGET - OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1)) / STAGE_BYTES;
         return n > TG2_MAX_STAGES ? TG2_MAX_STAGES : n;
     }
     static constexpr int total(bool has_res) {
-        return stages(has_res) * STAGE_BYTES + OUT_BYTES + ((has_res && RES_TMA) ? RES_BYTES : 0) + 256 + 1024;
+        return stages(has_res) * STAGE_BYTES + OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1) + 256 + 1024;
     }
 };
 
@@ -49,8 +46,7 @@ STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int
 STAR_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-STAR_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-STAR_DEVINL void epi_group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct TapGemm2Extra {
     int num_tiles;        // m_tiles * n_tiles
@@ -72,7 +68,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int OFF_OUT = NS * SM::STAGE_BYTES;
     const int OFF_RES = OFF_OUT + SM::OUT_BYTES;
     const bool res_tma = SM::RES_TMA && p.residual != nullptr;         // residual tile prefetched by TMA (else: direct loads)
-    const int OFF_BAR = OFF_RES + (res_tma ? SM::RES_BYTES : 0);
+    const int OFF_BAR = OFF_OUT + SM::OUT_BYTES * (res_tma ? 2 : 1);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + TG2_MAX_STAGES;
     uint64_t* acc_full = empty_bar + TG2_MAX_STAGES; // 2
@@ -207,11 +203,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int swz = (r >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
-        uint8_t* out_row = smem + OFF_OUT + ehalf * 16384 + r * 64;     // this group's two sub-tile buffers
+        uint8_t* out_row = smem + OFF_OUT + r * 64;
         const uint8_t* res_row = smem + OFF_RES + r * 64;
-        const bool leader = (threadIdx.x == (4 + 4 * ehalf) * 32);      // one store-issuing thread per group
-        const int gbar = 1 + ehalf;
-        int sbuf = 0;
+        const bool leader = (threadIdx.x == 4 * 32);
         int local = 0;
         for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
             int org[4], n_tile;
@@ -242,11 +236,15 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (res_tma) mbar_wait(res_full, local & 1);
             const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
             const int last_c0 = ((n_per_tile / 32 - 1 - ehalf) & ~1) * 32 + ehalf * 32;   // last chunk of this warp
+            constexpr int PASS_COLS = SM::OUT_COLS;
 #pragma unroll 1
-            for (int c0 = ehalf * 32; c0 < n_per_tile; c0 += 64) {
-                // the store issued two chunks ago (same buffer) must have finished reading shared memory
-                if (leader) tma_store_wait_read1();
-                epi_group_sync(gbar);
+            for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS) {
+            // the TMA stores of the previous pass / tile must have finished reading the staging buffer
+            if (leader) tma_store_wait_read();
+            epi_bar_sync();
+            const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
+#pragma unroll 1
+            for (int c0 = pass0 + ehalf * 32; c0 < pass_end; c0 += 64) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld32(t_row + c0, v);
@@ -311,7 +309,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                     }
                 }
-                const int sub = c0 >> 5;
+                const int sub = (c0 - pass0) >> 5;
                 if (res_tma) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -342,18 +340,21 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     o.y = pack_half2(f[u * 8 + 2], f[u * 8 + 3]);
                     o.z = pack_half2(f[u * 8 + 4], f[u * 8 + 5]);
                     o.w = pack_half2(f[u * 8 + 6], f[u * 8 + 7]);
-                    *reinterpret_cast<uint4*>(out_row + sbuf * 8192 + ((u ^ swz) * 16)) = o;
+                    *reinterpret_cast<uint4*>(out_row + sub * 8192 + ((u ^ swz) * 16)) = o;
                 }
-                fence_proxy_async_smem();
-                epi_group_sync(gbar);
-                if (leader) {
-                    if (n_base + c0 < p.N)
-                        tma_store_5d(&tmap_out, smem + OFF_OUT + ehalf * 16384 + sbuf * 8192, n_base + c0, org[0], org[1], org[2], org[3]);
-                    tma_store_commit();
-                }
-                sbuf ^= 1;
             }
-            if (res_tma) mbar_arrive(res_empty);
+            if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
+            fence_proxy_async_smem();
+            epi_bar_sync();
+            if (leader) {
+#pragma unroll 1
+                for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
+                    if (n_base + pass0 + sb * 32 < p.N)
+                        tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
+                }
+                tma_store_commit();
+            }
+            }
         }
         if (leader) tma_store_wait_all();
     }
