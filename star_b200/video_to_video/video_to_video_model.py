@@ -61,11 +61,11 @@ class VideoToVideo_sr():
             # ref :57-63 downloads stabilityai/stable-video-diffusion-img2vid (subfolder vae, variant fp16) through
             # diffusers; here the same checkpoint is read from a local snapshot into the sm_100a temporal VAE.
             from .modules.temporal_vae import AutoencoderKLTemporalDecoder
-            vae_path = getattr(opt, 'vae_path', None) or getattr(cfg, 'vae_path', None)
+            vae_path = _find_vae_dir(opt)
             if vae_path is None:
-                raise ValueError("VideoToVideo_sr: pass opt.vae_path (local snapshot of "
-                                 "stabilityai/stable-video-diffusion-img2vid/vae) or vae=...; "
-                                 "denoise_latents() needs neither")
+                raise ValueError("VideoToVideo_sr: no temporal-VAE weights found -- pass opt.vae_path, set STAR_VAE_PATH or "
+                                 "keep the snapshot the reference downloads (stabilityai/stable-video-diffusion-img2vid, "
+                                 "subfolder vae) in the Hugging Face cache; or pass vae=...  (denoise_latents() needs neither)")
             vae = AutoencoderKLTemporalDecoder.from_pretrained(vae_path, variant="fp16")
             vae.eval()
             vae.requires_grad_(False)
@@ -156,6 +156,19 @@ class VideoToVideo_sr():
             z_list.append(self.vae.encode(t[ind:ind + chunk_size]).latent_dist.sample())
         z = rearrange(torch.cat(z_list, dim=0), "(b f) c h w -> b c f h w", f=num_f)
         return z * self.vae.config.scaling_factor
+
+
+def _find_vae_dir(opt):
+    """opt.vae_path / cfg.vae_path / $STAR_VAE_PATH, else the snapshot the reference's from_pretrained call (ref :57-59)
+    leaves in the Hugging Face cache -- so that the reference's unmodified CLI, which only sets model_path, keeps working."""
+    import glob
+    import os
+    for cand in (getattr(opt, 'vae_path', None), getattr(cfg, 'vae_path', None), os.environ.get('STAR_VAE_PATH')):
+        if cand:
+            return cand
+    hub = os.environ.get('HF_HUB_CACHE') or os.path.join(os.environ.get('HF_HOME', os.path.expanduser('~/.cache/huggingface')), 'hub')
+    hits = sorted(glob.glob(os.path.join(hub, 'models--stabilityai--stable-video-diffusion-img2vid', 'snapshots', '*', 'vae')))
+    return hits[-1] if hits else None
 
 
 def _centre_pad(size, target):

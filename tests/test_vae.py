@@ -183,3 +183,29 @@ def test_pixel_pipeline_gpu():
     assert out.shape == (1, 3, 4, 128, 192) and out.dtype == torch.float32 and out.device.type == "cpu"
     assert torch.isfinite(out).all()
     assert torch.equal(outs[0], outs[1])            # same seed -> same video (posterior sample, diffuse noise, SDE noise)
+
+
+def test_vae_weights_lookup_and_from_pretrained(tmp_path, monkeypatch):
+    """from_pretrained reads a diffusers-layout directory; the pipeline finds it via opt / env / the HF cache layout"""
+    import json
+    from types import SimpleNamespace
+    from safetensors.torch import save_file
+    from star_b200.video_to_video.modules.temporal_vae import AutoencoderKLTemporalDecoder
+    from star_b200.video_to_video.video_to_video_model import _find_vae_dir
+    cfg, sd, _ = _setup(SMALL)
+    snap = tmp_path / "hub" / "models--stabilityai--stable-video-diffusion-img2vid" / "snapshots" / "abc" / "vae"
+    snap.mkdir(parents=True)
+    (snap / "config.json").write_text(json.dumps({"_class_name": "AutoencoderKLTemporalDecoder", "block_out_channels": [64, 64, 128, 128],
+                                                  "layers_per_block": 2, "latent_channels": 4, "scaling_factor": 0.18215,
+                                                  "down_block_types": ["DownEncoderBlock2D"] * 4}))
+    save_file({k: v.half().contiguous() for k, v in sd.items()}, str(snap / "diffusion_pytorch_model.fp16.safetensors"))
+    monkeypatch.delenv("STAR_VAE_PATH", raising=False)
+    monkeypatch.setenv("HF_HUB_CACHE", str(tmp_path / "hub"))
+    assert _find_vae_dir(SimpleNamespace(model_path="x")) == str(snap)
+    monkeypatch.setenv("STAR_VAE_PATH", "/somewhere/else")
+    assert _find_vae_dir(SimpleNamespace(model_path="x")) == "/somewhere/else"
+    assert _find_vae_dir(SimpleNamespace(vae_path="/explicit")) == "/explicit"
+    vae = AutoencoderKLTemporalDecoder.from_pretrained(str(snap), variant="fp16")
+    got = vae.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k].float(), sd[k].half().float()) for k in sd)
+    assert vae.config.block_out_channels == (64, 64, 128, 128)
