@@ -1,16 +1,20 @@
 // star_b200 / csrc / attn4.cuh
-// Fourth-generation spatial-attention kernel (head_dim 64): attn2's structure (two 128-row query tiles
-// per CTA sharing every K/V tile, thread = query row, single-pass softmax from TMEM, lazy max, O
-// accumulated in TMEM) with the probabilities kept in TENSOR MEMORY:
-//   * P_t(j) is written with tcgen05.st as packed fp16 pairs (64 columns per tile) and the PV MMA takes
-//     its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  The ncu capture of attn2
-//     (profiles/r01_ncu_attn2.txt) showed neither MUFU (54 %) nor issue slots (43 %) saturated; the
-//     shared-memory port was: per KV tile the SS formulation moves 256 KB through smem (Q, K, V operand
-//     reads, P written by threads and read back as the A operand, TMA fills) = 2048 clk at 128 B/clk,
-//     twice the MMA time.  Keeping P out of smem halves that.
-//   * the MMA thread issues both S(j+1) before waiting for either P(j) (no head-of-line blocking).
-//   * the 64 KB of smem freed by P deepen the K/V ring to 5 stages.
-// TMEM columns: S[t] t*128, O[t] 256 + t*64, P[t] 384 + t*64.
+// Spatial-attention kernel (head_dim 64): two 128-row query tiles per CTA share every K/V tile (5-stage TMA ring),
+// S = Q K^T in TMEM, single-pass online softmax with lazy rescale, O accumulated in TMEM, and the probabilities kept in
+// TENSOR MEMORY:
+//   * P_t(j) is written with tcgen05.st as packed fp16 pairs (64 columns per tile) and the PV MMA takes its A operand
+//     from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  The ncu capture of attn2 (profiles/r01_ncu_attn2.txt) showed
+//     the shared-memory port as the limiter of the SS formulation (256 KB per KV tile = 2048 clk at 128 B/clk, twice
+//     the MMA time); keeping P out of smem halves that.
+//   * two MMA-issuing threads (warp 1: query tile 0, warp 2: query tile 1): one independent S -> P -> PV pipeline per
+//     tile, descriptors built once and advanced by 64-bit adds.
+//   * softmax arithmetic in packed fp32x2 (FFMA2 / FADD2), compile-time specialisation of the ragged last KV tile.
+// Two softmax organisations (template SPLIT):
+//   SPLIT = 1 (default, 640 threads): two threads per query row -- score columns [0,64) / [64,128) of the KV tile,
+//             O columns [0,32) / [32,64); the halves agree on the row maximum through shared memory and one
+//             256-thread named barrier per KV tile.  16 softmax warps keep the 16-lane MUFU ~80 % busy.
+//   SPLIT = 0 (384 threads): one thread per row (128 score columns in registers), kept for comparison (STAR_ATTN_IMPL=4).
+// TMEM columns: S[t] t*128, O[t] 256 + t*64, P[t] 384 + t*64.  Measurements and the experiment log: DESIGN.md section 3.
 #pragma once
 #include "common.cuh"
 #include "attn.cuh"

@@ -5,7 +5,8 @@
 //   * the epilogue is fully coalesced: residual tile arrives by TMA (prefetched during the main loop),
 //     results are staged in swizzled shared memory and leave through TMA stores (hardware clips ragged
 //     tile edges and the N tail), bias / time-embedding rows are read with 128-bit loads
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
+// Tile widths BN = 128 / 160 / 256 (star_abi.cu picks: 256 wherever the padded width wastes little; 6 / 5 / 4 operand
+// stages).  Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
 // warps 4-11 epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and every other 32-column chunk
 // (the GEGLU / residual epilogues are instruction-bound with one warp per quadrant).
 #pragma once
