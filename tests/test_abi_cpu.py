@@ -32,3 +32,27 @@ def test_init_fails_loudly_without_gpu():
     from star_b200 import lib
     with pytest.raises(lib.StarError):
         lib.ensure_init(0)
+
+
+def test_every_op_has_a_kernel_reference_and_an_abi_entry():
+    """ops.py wrappers <-> oracle/kernel_ref.py twins (same names, compatible signatures) <-> exported C symbols"""
+    import inspect
+    from oracle import kernel_ref as KR
+    from star_b200 import lib as L
+    from star_b200 import ops
+    skip = {"trace_begin", "trace_end", "launch_count"}
+    names = [n for n, f in vars(ops).items() if inspect.isfunction(f) and not n.startswith("_") and n not in skip
+             and f.__module__ == ops.__name__]
+    assert len(names) >= 20
+    src = inspect.getsource(ops)
+    for n in names:
+        assert hasattr(KR, n), f"oracle/kernel_ref.py has no reference for ops.{n}"
+        po = list(inspect.signature(inspect.unwrap(getattr(ops, n))).parameters)
+        pr = list(inspect.signature(getattr(KR, n)).parameters)
+        n_common = min(len(po), len(pr))
+        diff = [i for i in range(n_common) if po[i] != pr[i]]
+        assert len(diff) <= 1 and abs(len(po) - len(pr)) <= 1, f"{n}: ops{po} vs kernel_ref{pr}"
+    used = {s for s in L.SIGNATURES if f"L.{s}(" in src or f"L.{s} " in src}
+    helpers = {"star_version", "star_last_error", "star_init", "star_launch_count"}
+    missing = [s for s in L.SIGNATURES if s not in used and s not in helpers]
+    assert not missing, f"C entry points without an ops wrapper: {missing}"
