@@ -103,3 +103,43 @@ def test_product_has_no_cpu_fallback():
     x = torch.zeros(8, 64, dtype=torch.float16)
     with pytest.raises(lib.StarError):
         ops.linear(x, x)
+
+
+def test_uneven_chunks_host_graph_vs_oracle(small_sd, monkeypatch):
+    """A 36-frame clip with max_chunk_len 16 -> chunks (0,16), (8,24), (16,36): the last one is 1.25x long (as the
+    (32,72) chunk of BASELINE config 3).  Product (host graph on emulated kernels, fp16 storage) against the fp32 oracle
+    UNet through the same sampler, CFG 7.5, identical noise."""
+    from oracle import kernel_ref as KR
+    from oracle.unet_ref import UNetCfg, controlled_unet_forward
+    from star_b200 import ops
+    from star_b200.video_to_video.diffusion.diffusion_sdedit import GaussianDiffusion
+    from star_b200.video_to_video.diffusion.schedules_sdedit import noise_schedule
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    from star_b200.video_to_video.video_to_video_model import make_chunks
+    for name in dir(KR):
+        if not name.startswith("_") and callable(getattr(KR, name)) and hasattr(ops, name):
+            monkeypatch.setattr(ops, name, getattr(KR, name))
+    chunks = make_chunks(36, 0, 16)
+    assert chunks == [(0, 16), (8, 24), (16, 36)]
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**SMALL_KW)
+    net.load_state_dict(small_sd, assign=True)
+    net = net.half().eval()
+    cfg = UNetCfg(**SMALL_KW)
+
+    def oracle_model(xt, t, y=None, hint=None, hint_chunk=None, variant_info=None):
+        return controlled_unet_forward(small_sd, xt, t, y, hint_chunk if hint_chunk is not None else hint, cfg)
+
+    x, hint, y = make_inputs(5, 1, 36, 10, 8)
+    _, _, ny = make_inputs(6, 1, 36, 10, 8)
+    diff = GaussianDiffusion(noise_schedule(schedule="logsnr_cosine_interp", n=1000, zero_terminal_snr=True, scale_min=2.0,
+                                            scale_max=4.0))
+    outs = []
+    for model in (oracle_model, net):
+        g = torch.Generator().manual_seed(3)
+        outs.append(diff.sample_sr(noise=x.clone(), model=model, model_kwargs=[{"y": y}, {"y": ny}, {"hint": hint}],
+                                   guide_scale=7.5, guide_rescale=0.2, solver="dpmpp_2m_sde", solver_mode="normal", steps=2,
+                                   t_max=899, t_min=0, discretization="trailing", chunk_inds=list(chunks),
+                                   noise_sampler=lambda a, b: torch.randn(x.shape, generator=g)).float())
+    err = rel_l2(outs[1], outs[0])
+    assert outs[1].shape == (1, 4, 36, 10, 8) and err < 1e-2, err          # CFG 7.5 amplifies the fp16 error (cf. test_unet_gpu)
