@@ -163,6 +163,140 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (NOT yet run on hardware): 74 clusters loop over the 256 x BN pair-tiles, two TMEM accumulators so that
+// the epilogue of tile i overlaps the MMAs of tile i+1.  New protocol element: the leader's MMA thread may only overwrite
+// an accumulator once the epilogue warps of BOTH CTAs have drained it -> acc_empty lives in the leader and the peer's
+// epilogue threads arrive on it remotely (shared::cluster address with the peer bit cleared).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_2cta_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                            __half* __restrict__ C, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;       // 2
+    uint64_t* acc_empty = acc_full + 2;            // 2 (leader's copies are the ones in use)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_tiles = (N + BN - 1) / BN, m_pairs = (M + 2 * BM - 1) / (2 * BM);
+    const int total = n_tiles * m_pairs;
+    const int k_iters = (K + BK - 1) / BK;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&acc_full[b], 1);
+                mbar_init(&acc_empty[b], 2 * 128);   // 4 epilogue warps of each CTA
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = cluster_id; t < total; t += n_clusters) {
+                const int n0 = (t % n_tiles) * BN;
+                const int m0 = ((t / n_tiles) * 2 + (int)rank) * BM;
+                for (int kc = 0; kc < k_iters; ++kc) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[s], 2u * STAGE_BYTES);
+                    tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], kc * BK, m0);
+                    tma_load_2d_2sm(sa + A_BYTES, &tmap_w, &full_bar[s], kc * BK, n0 + (int)rank * (BN / 2));
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, 0, 0);
+            const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+            const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + A_BYTES, 16, 1024);
+            constexpr uint64_t STAGE_INC = (uint64_t)(STAGE_BYTES >> 4);
+            int s = 0, local = 0;
+            uint32_t ph = 0;
+            for (int t = cluster_id; t < total; t += n_clusters, ++local) {
+                const int buf = local & 1;
+                mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * 256;
+                for (int kc = 0; kc < k_iters; ++kc) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = da0 + STAGE_INC * (uint64_t)s, db = db0 + STAGE_INC * (uint64_t)s;
+                    umma_f16_ss_2sm(acc, da, db, idesc, kc > 0 ? 1u : 0u);
+                    umma_f16_ss_2sm(acc, da + 2, db + 2, idesc, 1u);
+                    umma_f16_ss_2sm(acc, da + 4, db + 4, idesc, 1u);
+                    umma_f16_ss_2sm(acc, da + 6, db + 6, idesc, 1u);
+                    umma_commit_2sm(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_2sm(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int local = 0;
+        for (int t = cluster_id; t < total; t += n_clusters, ++local) {
+            const int buf = local & 1;
+            const int n0 = (t % n_tiles) * BN;
+            const long long row = (long long)((t / n_tiles) * 2 + (int)rank) * BM + r;
+            mbar_wait(&acc_full[buf], (local >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {                       // accumulator drained by this thread
+                    tc_fence_before();
+                    mbar_arrive_leader(&acc_empty[buf]);
+                }
+                if (row < M && n0 + c0 + 32 <= N) {
+                    uint4* dst = reinterpret_cast<uint4*>(C + row * N + n0 + c0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 o;
+                        o.x = pack_half2(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]));
+                        o.y = pack_half2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]));
+                        o.z = pack_half2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]));
+                        o.w = pack_half2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
+                        dst[u] = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 __global__ void ref_kernel(const __half* A, const __half* W, float* C, int M, int N, int K) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)M * N) return;
@@ -202,12 +336,20 @@ int main(int argc, char** argv) {
     cudaMemset(C, 0, (size_t)M * N * 2);
     const CUtensorMap ta = make_map(A, K, M, BM), tw = make_map(W, K, N, BN / 2);
     const int m_pairs = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
-    const size_t smem = STAGES * STAGE_BYTES + 256 + 1024;
+    const size_t smem = STAGES * STAGE_BYTES + 256 + 1024;       // barriers live in the 256 bytes behind the ring
     cudaFuncSetAttribute(gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const dim3 grid(2 * m_pairs * n_tiles);
-    gemm_2cta_kernel<<<grid, 192, smem>>>(ta, tw, C, M, N, K);
+    const bool persistent = argc > 3 && atoi(argv[3]) != 0;          // ./gemm_2cta M K 1 -> persistent variant
+    cudaFuncSetAttribute(gemm_2cta_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    const dim3 grid(persistent ? (unsigned)(prop.multiProcessorCount & ~1) : (unsigned)(2 * m_pairs * n_tiles));
+    auto launch = [&]() {
+        if (persistent) gemm_2cta_persistent_kernel<<<grid, 192, smem>>>(ta, tw, C, M, N, K);
+        else gemm_2cta_kernel<<<grid, 192, smem>>>(ta, tw, C, M, N, K);
+    };
+    launch();
     cudaError_t e = cudaDeviceSynchronize();
-    printf("gemm_2cta M=%d N=%d K=%d grid=%u: %s\n", M, N, K, grid.x, cudaGetErrorString(e));
+    printf("gemm_2cta%s M=%d N=%d K=%d grid=%u: %s\n", persistent ? " (persistent)" : "", M, N, K, grid.x, cudaGetErrorString(e));
     if (e != cudaSuccess) return 1;
     ref_kernel<<<(unsigned)(((long long)M * N + 255) / 256), 256>>>(A, W, R, M, N, K);
     cudaDeviceSynchronize();
@@ -224,7 +366,7 @@ int main(int argc, char** argv) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
-    for (int i = 0; i < 5; ++i) gemm_2cta_kernel<<<grid, 192, smem>>>(ta, tw, C, M, N, K);
+    for (int i = 0; i < 5; ++i) launch();
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms;
