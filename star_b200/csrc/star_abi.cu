@@ -20,6 +20,7 @@
 #include "tattn2.cuh"
 #include "tapgemm.cuh"
 #include "tapgemm2.cuh"
+#include "tapgemm2_pair.cuh"
 
 using namespace star;
 
@@ -35,7 +36,7 @@ int g_gemm_wide_waste_longk = 25;   // ... and for reductions >= 1920 (N = 640 a
 int g_gemm_wide_waste = 10;   // largest padding (percent of N) accepted for the 128x256 tiles (STAR_GEMM_WIDE_WASTE)
 int g_gemm_wide_mink = 256;   // smallest reduction length that takes the 128x256 tiles (STAR_GEMM_WIDE_MINK)
 int g_ln_impl = 0;         // 1 = one-row-per-warp LayerNorm for every width (debug override STAR_LN_IMPL)
-int g_gemm_pair = 0;       // 1: CTA-pair (cta_group::2) tiles for the N = k*160 layers, 2: also for BN = 128 (STAR_GEMM_PAIR; experimental)
+int g_gemm_pair = 0;       // 1: experimental CTA-pair (cta_group::2) tiles for the N = k*160 layers, 2: also BN = 128 (STAR_GEMM_PAIR)
 int g_gn_impl = 0;         // 1 = first-generation GroupNorm kernels (debug override STAR_GN_IMPL)
 int g_gemm_bn256 = 1;     // 128x256 persistent tiles where N % 256 == 0 (debug override STAR_GEMM_BN256=0)
 int g_attn_pingpong = 1;  // attn4 exp-phase ping-pong between the two softmax groups (debug override STAR_ATTN_PINGPONG)
@@ -163,7 +164,7 @@ int launch_tapgemm_bn(const TapDesc& d, cudaStream_t st) {
     return 0;
 }
 
-template <int BN, int PAIR = 0>
+template <int BN>
 int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     TapGemmParams p;
     memset(&p, 0, sizeof(p));
@@ -196,8 +197,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     const int n_per_tile = geglu ? BN / 2 : BN;
     TapGemm2Extra ex;
     ex.n_tiles = (d.N + n_per_tile - 1) / n_per_tile;
-    ex.m_tiles = (int)m_tiles;
-    const long long total = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * ex.n_tiles;        // PAIR: 256-row pair tiles
+    const long long total = m_tiles * ex.n_tiles;
     if (total > 0x7fffffffll) return fail("tapgemm2: too many tiles");
     ex.num_tiles = (int)total;
 
@@ -207,7 +207,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     const unsigned long long wrows = geglu ? 2ull * d.N : (unsigned long long)d.N;
     unsigned long long wdim[2] = {(unsigned long long)d.ntaps * d.K, wrows};
     unsigned long long wstr[2] = {1, (unsigned long long)d.ntaps * d.K};
-    unsigned wbox[2] = {TG_BK, (unsigned)((geglu || PAIR) ? BN / 2 : BN)};             // PAIR: each CTA loads half a tile
+    unsigned wbox[2] = {TG_BK, (unsigned)(geglu ? BN / 2 : BN)};
     if (make_tmap(&tw, d.W, 2, wdim, wstr, wbox)) return 1;
     // output / residual: (N, n1..n4) with row pitch ld; 32-column boxes, SWIZZLE_64B staging tiles
     unsigned obox[5] = {32, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
@@ -223,36 +223,105 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     unsigned long long ostr[5], rstr[5];
     strides(d.ldo, ostr);
     if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (d.residual && TapGemm2Smem<BN, PAIR>::RES_TMA) {
+    if (d.residual && TapGemm2Smem<BN>::RES_TMA) {
         strides(d.ldres, rstr);
         if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
         tr = to;
     }
-    ex.stages = TapGemm2Smem<BN, PAIR>::stages(d.residual != nullptr);
-    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
-    if (PAIR) {
-        // clusters of two CTAs (one TPC); an even grid, one cluster per pair tile at most
-        const int grid = (int)std::min<long long>(2 * total, (long long)(g_num_sms & ~1));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(TG2_THREADS);
-        cfg.dynamicSmemBytes = TapGemm2Smem<BN, PAIR>::total(d.residual != nullptr);
-        cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        STAR_CUDA(cudaLaunchKernelEx(&cfg, tapgemm2_kernel<BN, PAIR>, ta, tw, to, tr, p, ex));
-        g_launches.fetch_add(1);
-        return 0;
-    }
     const int grid = (int)std::min<long long>(total, g_num_sms);
-    tapgemm2_kernel<BN, PAIR><<<grid, TG2_THREADS, TapGemm2Smem<BN, PAIR>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
+    ex.stages = TapGemm2Smem<BN>::stages(d.residual != nullptr);
+    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
+    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
+    return 0;
+}
+
+// experimental CTA-pair configuration (tapgemm2_pair.cuh), reached only with STAR_GEMM_PAIR
+template <int BN>
+int launch_tapgemm2_pair_bn(const TapDesc& d, cudaStream_t st) {
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    long long m_tiles = 1;
+    int box_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.on[i] = d.on[i];
+        p.box[i] = d.box[i];
+        p.tiles[i] = (d.on[i] + d.box[i] - 1) / d.box[i];
+        m_tiles *= p.tiles[i];
+        box_rows *= d.box[i];
+    }
+    if (box_rows > TG_BM) return fail("tapgemm2: box has %d rows (> %d)", box_rows, TG_BM);
+    p.box_rows = box_rows;
+    p.ntaps = d.ntaps;
+    memcpy(p.tap, d.tap, sizeof(p.tap));
+    p.K = d.K;
+    p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
+    p.N = d.N;
+    p.flags = d.flags | g_gemm_flags;
+    p.bias = (const __half*)d.bias;
+    p.rowvec = (const __half*)d.rowvec;
+    p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
+    p.residual = (const __half*)d.residual;
+    p.colscale = (const __half*)d.colscale;
+    p.res_ld = d.ldres;
+    p.out = (__half*)d.out;
+    p.out_ld = d.ldo;
+    const bool geglu = d.flags & TG_GEGLU;
+    const int n_per_tile = geglu ? BN / 2 : BN;
+    TapGemm2PairExtra ex;
+    ex.n_tiles = (d.N + n_per_tile - 1) / n_per_tile;
+    ex.m_tiles = (int)m_tiles;
+    const long long total = (m_tiles + 1) / 2 * ex.n_tiles;                   // 256-row pair tiles
+    if (total > 0x7fffffffll) return fail("tapgemm2: too many tiles");
+    ex.num_tiles = (int)total;
+
+    CUtensorMap ta, tw, to, tr;
+    unsigned abox[5] = {TG_BK, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
+    if (make_tmap(&ta, d.A, 5, d.adim, d.astr, abox)) return 1;
+    const unsigned long long wrows = geglu ? 2ull * d.N : (unsigned long long)d.N;
+    unsigned long long wdim[2] = {(unsigned long long)d.ntaps * d.K, wrows};
+    unsigned long long wstr[2] = {1, (unsigned long long)d.ntaps * d.K};
+    unsigned wbox[2] = {TG_BK, (unsigned)(BN / 2)};                                  // each CTA loads half a weight tile
+    if (make_tmap(&tw, d.W, 2, wdim, wstr, wbox)) return 1;
+    // output / residual: (N, n1..n4) with row pitch ld; 32-column boxes, SWIZZLE_64B staging tiles
+    unsigned obox[5] = {32, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
+    unsigned long long odim[5] = {(unsigned long long)d.N, (unsigned long long)d.on[0], (unsigned long long)d.on[1],
+                                  (unsigned long long)d.on[2], (unsigned long long)d.on[3]};
+    auto strides = [&](long long ld, unsigned long long* s) {
+        s[0] = 1;
+        s[1] = (unsigned long long)ld;
+        s[2] = s[1] * d.on[0];
+        s[3] = s[2] * d.on[1];
+        s[4] = s[3] * d.on[2];
+    };
+    unsigned long long ostr[5], rstr[5];
+    strides(d.ldo, ostr);
+    if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (d.residual && TapGemm2PairSmem<BN>::RES_TMA) {
+        strides(d.ldres, rstr);
+        if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    } else {
+        tr = to;
+    }
+    ex.stages = TapGemm2PairSmem<BN>::stages(d.residual != nullptr);
+    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
+    // clusters of two CTAs (one TPC): an even grid, at most one cluster per pair tile
+    const int grid = (int)std::min<long long>(2 * total, (long long)(g_num_sms & ~1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TG2_THREADS);
+    cfg.dynamicSmemBytes = TapGemm2PairSmem<BN>::total(d.residual != nullptr);
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    STAR_CUDA(cudaLaunchKernelEx(&cfg, tapgemm2_pair_kernel<BN>, ta, tw, to, tr, p, ex));
+    STAR_LAUNCH_CHECK("tapgemm2_pair");
     return 0;
 }
 
@@ -276,12 +345,9 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
                       g_gemm_bn256 != 0 && !(geglu && g_gemm_bn256 == 2) && g_gemm_impl != 1;
     if (wide) return launch_tapgemm2_bn<256>(d, st);
     if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
-        if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) {
-            if (g_gemm_pair) return launch_tapgemm2_bn<160, 1>(d, st);       // experimental CTA-pair tiles (STAR_GEMM_PAIR=1)
-            return launch_tapgemm2_bn<160>(d, st);
-        }
-        if (g_gemm_pair == 2) return launch_tapgemm2_bn<128, 1>(d, st);
-        return launch_tapgemm2_bn<128>(d, st);
+        if (!geglu && d.N % 160 == 0 && d.N % 128 != 0)
+            return g_gemm_pair ? launch_tapgemm2_pair_bn<160>(d, st) : launch_tapgemm2_bn<160>(d, st);
+        return g_gemm_pair == 2 ? launch_tapgemm2_pair_bn<128>(d, st) : launch_tapgemm2_bn<128>(d, st);
     }
     if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm_bn<160>(d, st);
     return launch_tapgemm_bn<128>(d, st);
@@ -332,8 +398,8 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true))));
-    STAR_CUDA((cudaFuncSetAttribute(tapgemm2_kernel<160, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160, 1>::total(false), TapGemm2Smem<160, 1>::total(true)))));
-    STAR_CUDA((cudaFuncSetAttribute(tapgemm2_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128, 1>::total(false), TapGemm2Smem<128, 1>::total(true)))));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<160>::total(false), TapGemm2PairSmem<160>::total(true))));
+    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<128>::total(false), TapGemm2PairSmem<128>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));

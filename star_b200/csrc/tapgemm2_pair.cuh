@@ -1,27 +1,84 @@
-// star_b200 / csrc / tapgemm2.cuh
-// Persistent tap-GEMM (same contraction as tapgemm.cuh, see there for the tap / box addressing):
-//   * one CTA per SM loops over output tiles (n fastest, so concurrently running CTAs share the A tile in L2)
-//   * TMEM holds TWO accumulators: the epilogue of tile i runs while the MMAs of tile i+1 are issued
-//   * the epilogue is fully coalesced: residual tile arrives by TMA (prefetched during the main loop),
-//     results are staged in swizzled shared memory and leave through TMA stores (hardware clips ragged
-//     tile edges and the N tail), bias / time-embedding rows are read with 128-bit loads
-// Tile widths BN = 128 / 160 / 256 (star_abi.cu picks: 256 wherever the padded width wastes little; 6 / 5 / 4 operand
-// stages).  Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
-// warps 4-11 epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and every other 32-column chunk
-// (the GEGLU / residual epilogues are instruction-bound with one warp per quadrant).
+// star_b200 / csrc / tapgemm2_pair.cuh
+// EXPERIMENTAL, OFF BY DEFAULT (STAR_GEMM_PAIR=1), COMPILED BUT NOT YET RUN ON HARDWARE.
+// CTA-pair version of the persistent tap-GEMM of tapgemm2.cuh: the kernel is launched as clusters of two CTAs (two SMs of
+// one TPC); a pair computes a 256 x BN tile with tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its
+// own 128 rows of A and HALF of the weight tile (per k-block 16 KB + BN/2 x 128 B instead of 16 KB + BN x 128 B through L2
+// and shared memory), keeps its own accumulators, epilogue and output rows.  This is the route to wide-tile efficiency
+// for the 320-channel layers (N = 320 = 2 x 160 cannot fill a 128 x 256 tile).  The PROTOCOL (2-SM TMA loads crediting the
+// leader's barrier through the peer-bit mask, cta_group::2 alloc / mma / multicast commit) is validated stand-alone in
+// tools/micro/gemm_2cta.cu (profiles/r01_micro_gemm_2cta_prototype.log); its integration below (tap / box addressing,
+// two accumulators with remote acc_empty arrives, the staged TMA-store epilogue, GEGLU halves) is not.
+// Kept as a separate copy of the kernel -- rather than a template parameter of tapgemm2_kernel -- so that the validated
+// default kernel stays byte-identical until this one has passed the GPU suite; to be merged afterwards.
 #pragma once
-#include "common.cuh"
-#include "tapgemm.cuh"
+#include "tapgemm2.cuh"
 
 namespace star {
 
-constexpr int TG2_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle; warps 4-11: epilogue (two warps per TMEM lane quadrant)
-constexpr int TG2_MAX_STAGES = 6;
+// ---- CTA-pair (tcgen05 cta_group::2) helpers; protocol validated stand-alone in tools/micro/gemm_2cta.cu ----------
+constexpr uint32_t TG2_PEER_MASK = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address: "the leader's copy"
+STAR_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+STAR_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// data lands in THIS CTA's shared memory, the completion bytes are credited to the LEADER's barrier
+STAR_DEVINL void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & TG2_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+STAR_DEVINL void tma_load_5d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & TG2_PEER_MASK), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+STAR_DEVINL void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
+STAR_DEVINL void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+STAR_DEVINL void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TG2_PEER_MASK) : "memory");
+}
+template <uint32_t kCols>
+STAR_DEVINL void tmem_alloc_2sm(uint32_t* dst_in_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_in_smem)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+STAR_DEVINL void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
 
-template <int BN>
-struct TapGemm2Smem {
+struct TapGemm2PairExtra {
+    int num_tiles;        // pair tiles: ceil(m_tiles / 2) * n_tiles
+    int n_tiles;
+    int stages;           // operand ring depth
+    int m_tiles;          // number of 128-row tiles
+};
+
+template <int BN, int PAIR = 1>
+struct TapGemm2PairSmem {
     static constexpr int A_BYTES = TG_BM * TG_BK * 2;
-    static constexpr int B_BYTES = BN * TG_BK * 2;
+    static constexpr int B_BYTES = (BN >> PAIR) * TG_BK * 2;          // PAIR: each CTA stages half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // BN = 256 (48 KB stages): the staging buffer holds 128 output columns and the epilogue makes two passes over it,
     // and the residual is read straight from global memory -- that leaves room for 4 operand stages.
@@ -39,28 +96,17 @@ struct TapGemm2Smem {
     }
 };
 
-STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                 : "memory");
-}
-STAR_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-STAR_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-STAR_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-struct TapGemm2Extra {
-    int num_tiles;        // m_tiles * n_tiles
-    int n_tiles;
-    int stages;           // operand ring depth (depends on BN and on whether a residual buffer is needed)
-};
-
-template <int BN>
+// Same structure as tapgemm2_kernel; every loop iterates over PAIR tiles (PAIR is fixed to 1 here).
+template <int BN, int PAIR = 1>
 __global__ void __launch_bounds__(TG2_THREADS, 1)
-tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+tapgemm2_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                const __grid_constant__ TapGemmParams p, const __grid_constant__ TapGemm2Extra ex) {
-    using SM = TapGemm2Smem<BN>;
+                const __grid_constant__ TapGemmParams p, const __grid_constant__ TapGemm2PairExtra ex) {
+    using SM = TapGemm2PairSmem<BN, PAIR>;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // first (pair) tile and stride of this CTA
+    const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;          // TMEM columns between the two accumulators
     constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
     extern __shared__ uint8_t smem_raw[];
@@ -99,37 +145,46 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&acc_full[b], 1);
-                mbar_init(&acc_empty[b], 256);
+                mbar_init(&acc_empty[b], PAIR ? 512 : 256);      // PAIR: the epilogue threads of both CTAs (leader's copy)
             }
             mbar_init(res_full, 1);
             mbar_init(res_empty, 256);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<TMEM_COLS>(tmem_slot);
+        if constexpr (PAIR) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+        else tmem_alloc<TMEM_COLS>(tmem_slot);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();             // both CTAs' barriers exist before any remote arrive / TMA completion
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    auto tile_origin = [&](int tile, int* org, int& n_tile) {
+    auto tile_origin = [&](int tile, int* org, int& n_tile) -> bool {
         n_tile = tile % ex.n_tiles;
         int m_tile = tile / ex.n_tiles;
+        bool valid = true;
+        if constexpr (PAIR) {
+            m_tile = m_tile * 2 + (int)rank;
+            valid = m_tile < ex.m_tiles;
+            if (!valid) m_tile = 0;                      // odd tile count: the spare CTA re-reads tile 0 and stores nothing
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             org[i] = (m_tile % p.tiles[i]) * p.box[i];
             m_tile /= p.tiles[i];
         }
+        return valid;
     };
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)p.box_rows * 128u + (uint32_t)SM::B_BYTES;
+            const uint32_t tx = ((uint32_t)p.box_rows * 128u + (uint32_t)SM::B_BYTES) << PAIR;   // PAIR: both CTAs' bytes
             int s = 0, local = 0;
             uint32_t ph = 0;                              // ring phase (no runtime div/mod in the issue loops)
-            for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+            for (int tile = tile0; tile < ex.num_tiles; tile += tstep, ++local) {
                 int org[4], n_tile;
                 tile_origin(tile, org, n_tile);
                 for (int t = 0; t < p.ntaps; ++t) {
@@ -139,14 +194,22 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         uint8_t* sa = smem + s * SM::STAGE_BYTES;
                         uint8_t* sb = sa + SM::A_BYTES;
-                        mbar_expect_tx(&full_bar[s], tx);
-                        tma_load_5d(sa, &tmap_a, &full_bar[s], kc * TG_BK, c1, c2, c3, c4);
                         const int kw = t * p.K + kc * TG_BK;
-                        if (!geglu) {
-                            tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * BN);
+                        if constexpr (PAIR) {
+                            // accumulator columns [rank*BN/2, +BN/2) come from this CTA's half of the weight tile
+                            if (rank == 0) mbar_expect_tx(&full_bar[s], tx);
+                            tma_load_5d_2sm(sa, &tmap_a, &full_bar[s], kc * TG_BK, c1, c2, c3, c4);
+                            const int wrow = geglu ? (int)rank * p.N + n_tile * (BN / 2) : n_tile * BN + (int)rank * (BN / 2);
+                            tma_load_2d_2sm(sb, &tmap_w, &full_bar[s], kw, wrow);
                         } else {
-                            tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * (BN / 2));
-                            tma_load_2d(sb + (BN / 2) * 128, &tmap_w, &full_bar[s], kw, p.N + n_tile * (BN / 2));
+                            mbar_expect_tx(&full_bar[s], tx);
+                            tma_load_5d(sa, &tmap_a, &full_bar[s], kc * TG_BK, c1, c2, c3, c4);
+                            if (!geglu) {
+                                tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * BN);
+                            } else {
+                                tma_load_2d(sb, &tmap_w, &full_bar[s], kw, n_tile * (BN / 2));
+                                tma_load_2d(sb + (BN / 2) * 128, &tmap_w, &full_bar[s], kw, p.N + n_tile * (BN / 2));
+                            }
                         }
                         if (++s == NS) { s = 0; ph ^= 1; }
                     }
@@ -168,8 +231,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(TG_BM, BN, 0, 0);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(TG_BM << PAIR, BN, 0, 0);
             // The single issuing thread is on the critical path (ncu: tensor pipe 40 % busy with L2 at 50 % when each
             // k-step rebuilt two 64-bit descriptors): descriptors are formed once, a stage / k-step is a 64-bit add.
             const uint64_t desc_a0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
@@ -177,7 +240,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             constexpr uint64_t STAGE_INC = (uint64_t)(SM::STAGE_BYTES >> 4);
             int s = 0, local = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+            for (int tile = tile0; tile < ex.num_tiles; tile += tstep, ++local) {
                 const int buf = local & 1;
                 mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -187,14 +250,23 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc_fence_after();
                     const uint64_t da = desc_a0 + STAGE_INC * (uint64_t)s;
                     const uint64_t db = desc_b0 + STAGE_INC * (uint64_t)s;
-                    umma_f16_ss(acc, da, db, idesc, i > 0 ? 1u : 0u);
-                    umma_f16_ss(acc, da + 2, db + 2, idesc, 1u);
-                    umma_f16_ss(acc, da + 4, db + 4, idesc, 1u);
-                    umma_f16_ss(acc, da + 6, db + 6, idesc, 1u);
-                    umma_commit(&empty_bar[s]);
+                    if constexpr (PAIR) {
+                        umma_f16_ss_2sm(acc, da, db, idesc, i > 0 ? 1u : 0u);
+                        umma_f16_ss_2sm(acc, da + 2, db + 2, idesc, 1u);
+                        umma_f16_ss_2sm(acc, da + 4, db + 4, idesc, 1u);
+                        umma_f16_ss_2sm(acc, da + 6, db + 6, idesc, 1u);
+                        umma_commit_2sm(&empty_bar[s]);
+                    } else {
+                        umma_f16_ss(acc, da, db, idesc, i > 0 ? 1u : 0u);
+                        umma_f16_ss(acc, da + 2, db + 2, idesc, 1u);
+                        umma_f16_ss(acc, da + 4, db + 4, idesc, 1u);
+                        umma_f16_ss(acc, da + 6, db + 6, idesc, 1u);
+                        umma_commit(&empty_bar[s]);
+                    }
                     if (++s == NS) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&acc_full[buf]);
+                if constexpr (PAIR) umma_commit_2sm(&acc_full[buf]);
+                else umma_commit(&acc_full[buf]);
             }
         }
     } else if (warp >= 4) {
@@ -208,9 +280,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint8_t* res_row = smem + OFF_RES + r * 64;
         const bool leader = (threadIdx.x == 4 * 32);
         int local = 0;
-        for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
+        for (int tile = tile0; tile < ex.num_tiles; tile += tstep, ++local) {
             int org[4], n_tile;
-            tile_origin(tile, org, n_tile);
+            const bool tile_valid = tile_origin(tile, org, n_tile);
             const int buf = local & 1;
             const int n_base = n_tile * n_per_tile;
             // global output row of this tile row (clamped to the tensor for clipped rows): time-embedding row
@@ -282,7 +354,8 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
                 if (c0 == last_c0) {                         // last TMEM read of this warp for this accumulator
                     tc_fence_before();
-                    mbar_arrive(&acc_empty[buf]);
+                    if constexpr (PAIR) mbar_arrive_leader(&acc_empty[buf]);
+                    else mbar_arrive(&acc_empty[buf]);
                 }
                 if (p.flags & TG_GELU_TANH) {
 #pragma unroll
@@ -350,7 +423,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (leader) {
 #pragma unroll 1
                 for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
-                    if (n_base + pass0 + sb * 32 < p.N)
+                    if (n_base + pass0 + sb * 32 < p.N && tile_valid)
                         tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
                 }
                 tma_store_commit();
@@ -359,10 +432,12 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         if (leader) tma_store_wait_all();
     }
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();             // the peer's shared memory must outlive the leader's last MMA
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        if constexpr (PAIR) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+        else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
