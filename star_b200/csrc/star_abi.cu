@@ -398,8 +398,6 @@ int star_init(int device) {
     STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true))));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<160>::total(false), TapGemm2PairSmem<160>::total(true))));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<128>::total(false), TapGemm2PairSmem<128>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true))));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
     STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
@@ -425,6 +423,10 @@ int star_init(int device) {
     if (const char* e = getenv("STAR_GEMM_BN256")) g_gemm_bn256 = atoi(e);
     if (const char* e = getenv("STAR_GN_IMPL")) g_gn_impl = atoi(e);
     if (const char* e = getenv("STAR_GEMM_PAIR")) g_gemm_pair = atoi(e);
+    if (g_gemm_pair) {            // the experimental pair kernels are not touched at all unless asked for
+        STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<160>::total(false), TapGemm2PairSmem<160>::total(true))));
+        STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<128>::total(false), TapGemm2PairSmem<128>::total(true))));
+    }
     if (const char* e = getenv("STAR_LN_IMPL")) g_ln_impl = atoi(e);
     if (const char* e = getenv("STAR_GEMM_WIDE_MINK")) g_gemm_wide_mink = atoi(e);
     if (const char* e = getenv("STAR_GEMM_WIDE_WASTE")) g_gemm_wide_waste = atoi(e);
