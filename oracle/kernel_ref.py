@@ -104,6 +104,24 @@ def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=No
     return res
 
 
+def attention_exact(q, k, v, batch, heads, Nq, Nk, scale=0.125, budget_bytes=6 << 30):
+    """softmax(q k^T * scale) v in true fp32 with plain matmuls over query-row chunks (no fused kernel: a fused fp32
+    SDPA may run TF32 tensor ops).  k / v hold ONE kv batch shared by every q batch (kv_batch_div = batch) or `batch`."""
+    d = 64
+    qf = _f(q)[:, :heads * d].reshape(batch, Nq, heads, d).permute(0, 2, 1, 3)             # b h nq d
+    kvb = k.shape[0] // Nk
+    kf = _f(k)[:, :heads * d].reshape(kvb, Nk, heads, d).permute(0, 2, 3, 1)               # b h d nk
+    vf = _f(v)[:, :heads * d].reshape(kvb, Nk, heads, d).permute(0, 2, 1, 3)
+    if kvb != batch:
+        kf, vf = kf.expand(batch, -1, -1, -1), vf.expand(batch, -1, -1, -1)
+    out = torch.empty(batch, heads, Nq, d, device=q.device, dtype=torch.float32)
+    rows = max(1, min(Nq, budget_bytes // (4 * batch * heads * Nk)))
+    for r in range(0, Nq, rows):
+        s = torch.matmul(qf[:, :, r:r + rows], kf) * scale
+        out[:, :, r:r + rows] = torch.matmul(torch.softmax(s, dim=-1), vf)
+    return out.permute(0, 2, 1, 3).reshape(batch * Nq, heads * d).to(HALF)
+
+
 def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
     d = 64
     x = _f(qkv).reshape(B, T, HW, -1)

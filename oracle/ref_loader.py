@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE -- load the UNMODIFIED reference (NJU-PCALab/STAR) hot path.
 
-Only usable where /root/reference exists (the build container).  No reference
-source is copied: the files are executed where they lie, after five tiny
-import shims for packages that are absent from this image:
+Usable where /root/reference exists (the build container) or where oracle/stage_reference.py
+has staged the same unmodified files into the git-ignored oracle/_ref/ (the GPU box: GPU-side
+reference baseline and config-2 parity).  No reference source enters the repository: the files
+are executed where they lie, after five tiny import shims for packages absent from this image:
 
   xformers.ops.memory_efficient_attention -> F.scaled_dot_product_attention
       (call sites: video_to_video/modules/unet_v2v.py:179,184; semantics are
@@ -23,7 +24,20 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("STAR_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/stage_reference.py (git-ignored)
+
+
+def _find_root():
+    env = os.environ.get("STAR_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "video_to_video/modules/unet_v2v.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
@@ -46,8 +60,31 @@ class InjectedBrownian:
         return n.to(self.device, self.dtype) * (torch.as_tensor(t1) - torch.as_tensor(t0)).abs().sqrt().to(self.device)
 
 
+def _exact_attention_fp32(q, k, v, budget_bytes=8 << 30):
+    """softmax(q k^T / sqrt(d)) v in true fp32 (no fused kernel, whose fp32 path may run TF32 tensor ops):
+    batched matmuls over query-row chunks sized so the score block stays under ``budget_bytes``."""
+    Bh, Nq, d = q.shape
+    Nk = k.shape[1]
+    rows = max(1, min(Nq, budget_bytes // (4 * Bh * Nk)))
+    if rows < 16:                                   # many small heads (temporal attention): chunk the batch instead
+        out = torch.empty_like(q)
+        step = max(1, budget_bytes // (4 * Nq * Nk))
+        for b in range(0, Bh, step):
+            s = torch.baddbmm(q.new_zeros(()), q[b:b + step], k[b:b + step].transpose(1, 2), beta=0, alpha=d ** -0.5)
+            out[b:b + step] = torch.bmm(torch.softmax(s, dim=-1), v[b:b + step])
+        return out
+    out = torch.empty_like(q)
+    kt = k.transpose(1, 2)
+    for r in range(0, Nq, rows):
+        s = torch.bmm(q[:, r:r + rows], kt) * (d ** -0.5)
+        out[:, r:r + rows] = torch.bmm(torch.softmax(s, dim=-1), v)
+    return out
+
+
 def _mea(q, k, v, attn_bias=None, op=None):
     assert attn_bias is None
+    if q.is_cuda and q.dtype == torch.float32:
+        return _exact_attention_fp32(q, k, v)
     return F.scaled_dot_product_attention(q[None], k[None], v[None])[0]
 
 

@@ -32,8 +32,6 @@ struct AttnParams {
     float scale_log2;       // softmax scale * log2(e)
     __half* out;
     long long ldo;          // elements between consecutive rows of O
-    int order;              // attn4 MMA issue order: 0 = S,S,PV,PV per KV tile; 1 = S0,PV1,S1,PV0 (anti-phase)
-    int pingpong;           // attn4: softmax groups take turns on the exp phase (1) or run freely (0)
 };
 
 // SINGLE = the whole key range is one KV tile (text cross-attention, Nk = 77): no rings, one S / P / O buffer,

@@ -3,33 +3,22 @@
 // S = Q K^T in TMEM, single-pass online softmax with lazy rescale, O accumulated in TMEM, and the probabilities kept in
 // TENSOR MEMORY:
 //   * P_t(j) is written with tcgen05.st as packed fp16 pairs (64 columns per tile) and the PV MMA takes its A operand
-//     from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  The ncu capture of attn2 (profiles/r01_ncu_attn2.txt) showed
-//     the shared-memory port as the limiter of the SS formulation (256 KB per KV tile = 2048 clk at 128 B/clk, twice
-//     the MMA time); keeping P out of smem halves that.
+//     from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  The ncu capture of the SS formulation (profiles/r01_ncu_attn2.txt)
+//     showed the shared-memory port as its limiter (256 KB per KV tile = 2048 clk at 128 B/clk, twice the MMA time);
+//     keeping P out of smem halves that.
 //   * two MMA-issuing threads (warp 1: query tile 0, warp 2: query tile 1): one independent S -> P -> PV pipeline per
 //     tile, descriptors built once and advanced by 64-bit adds.
 //   * softmax arithmetic in packed fp32x2 (FFMA2 / FADD2), compile-time specialisation of the ragged last KV tile.
-// Two softmax organisations (template SPLIT):
-//   SPLIT = 1 (default, 640 threads): two threads per query row -- score columns [0,64) / [64,128) of the KV tile,
-//             O columns [0,32) / [32,64); the halves agree on the row maximum through shared memory and one
-//             256-thread named barrier per KV tile.  16 softmax warps keep the 16-lane MUFU ~80 % busy.
-//   SPLIT = 0 (384 threads): one thread per row (128 score columns in registers), kept for comparison (STAR_ATTN_IMPL=4).
-// TMEM columns: S[t] t*128, O[t] 256 + t*64, P[t] 384 + t*64.  Measurements and the experiment log: DESIGN.md section 3.
+//   * two softmax threads per query row (640 threads): score columns [0,64) / [64,128) of the KV tile, O columns
+//     [0,32) / [32,64); the halves agree on the row maximum through shared memory and one 256-thread named barrier
+//     per KV tile.  16 softmax warps keep the 16-lane MUFU ~80 % busy (every exponential on the MUFU: the FMA-pipe
+//     polynomial share and the one-thread-per-row organisation were measured and lost).
+// TMEM columns: S[t] t*128, O[t] 256 + t*64, P[t] 384 + t*64.
 #pragma once
 #include "common.cuh"
 #include "attn.cuh"
-#include "attn2.cuh"
 
 namespace star {
-
-// which of the 64 probability pairs of a row take the FMA-pipe polynomial instead of MUFU.EX2:
-// POLY_EVERY 0 none, 4 -> 1/4, 3 -> 1/3, 2 -> 1/2, 38 -> 3/8 (pairs 2, 5, 7 of every 8)
-template <int POLY_EVERY>
-STAR_DEVINL constexpr bool poly_slot(int e) {
-    if (POLY_EVERY == 38) return (e & 7) == 2 || (e & 7) == 5 || (e & 7) == 7;
-    if (POLY_EVERY <= 0 || POLY_EVERY == 16) return false;
-    return (e % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == POLY_EVERY - 1;
-}
 
 STAR_DEVINL void a4_st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 STAR_DEVINL float a4_ld_shared_f32(uint32_t addr) {
@@ -42,8 +31,7 @@ STAR_DEVINL void a4_named_bar_sync(int id, int nthreads) { asm volatile("bar.syn
 struct TagFalse { static constexpr bool value = false; };
 struct TagTrue { static constexpr bool value = true; };
 
-constexpr int A4_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle (one warpgroup, registers donated); 4-7 / 8-11: softmax
-constexpr int A4S_THREADS = 640;     // SPLIT: warps 4-11 query tile 0 (4-7 low score half, 8-11 high half), 12-19 query tile 1
+constexpr int A4S_THREADS = 640;     // warps 0-3: TMA, MMA x2, idle; warps 4-11 query tile 0 (4-7 low score half, 8-11 high half), 12-19 query tile 1
 constexpr int A4_KV_STAGES = 5;
 
 struct Attn4Smem {
@@ -56,14 +44,7 @@ struct Attn4Smem {
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-// SPLIT = 1: every query row is handled by TWO softmax threads (score columns [0,64) / [64,128) of the KV tile, O columns
-// [0,32) / [32,64)), 16 softmax warps, 640 threads.  The ncu source view of the SPLIT = 0 kernel shows the two softmax
-// warps of each scheduler busy ~100 % of the time at ~3 clk per instruction (in-order issue, dependent chains) with no
-// pipe saturated (XU 55 %, tensor 36 %, issue 64 %): the limiter is per-warp latency, i.e. too little thread-level
-// parallelism per scheduler; four half-length streams per scheduler attack exactly that.  The halves agree on the row
-// maximum through shared memory and one 256-thread named barrier per KV tile (as attn3.cuh did, but with P in TMEM).
-template <int POLY_EVERY, int SPLIT = 0>      // every POLY_EVERY-th exponential uses ex2_poly (0 = never)
-__global__ void __launch_bounds__(SPLIT ? A4S_THREADS : A4_THREADS, 1)
+__global__ void __launch_bounds__(A4S_THREADS, 1)
 attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -76,8 +57,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint64_t* s_free = bars + 13;            // 2   softmax WG t -> MMA : S_t(j) is in registers
     uint64_t* p_full = bars + 15;            // 2   softmax WG t -> MMA : P_t(j) in TMEM, O_t rescaled
     uint64_t* pv_done = bars + 17;           // 2   MMA -> softmax WG t : O_t += P_t(j) V_j retired
-    uint64_t* turn = bars + 19;              // 2   softmax WG (1-t) -> WG t : "your turn on the MUFU" (exp-phase ping-pong)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -98,14 +78,13 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_init(q_full, 1);
             for (int s = 0; s < A4_KV_STAGES; ++s) {
                 mbar_init(&kv_full[s], 1);
-                mbar_init(&kv_empty[s], (p.order == 2 && ntq > 1) ? 2 : 1);
+                mbar_init(&kv_empty[s], ntq > 1 ? 2 : 1);
             }
             for (int t = 0; t < 2; ++t) {
                 mbar_init(&s_full[t], 1);
-                mbar_init(&s_free[t], SPLIT ? 256 : 128);
-                mbar_init(&p_full[t], SPLIT ? 256 : 128);
+                mbar_init(&s_free[t], 256);
+                mbar_init(&p_full[t], 256);
                 mbar_init(&pv_done[t], 1);
-                mbar_init(&turn[t], 128);
             }
             fence_barrier_init();
         }
@@ -153,7 +132,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
-            for (int t = 0; t < ((p.order == 2) ? 1 : ntq); ++t) issue_s(t, 0);
+            issue_s(0, 0);
             auto issue_pv = [&](int t, int j) {
                 mbar_wait(&p_full[t], j & 1);
                 tc_fence_after();
@@ -169,49 +148,19 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 tc_fence_after();
                 issue_s(t, j + 1);
             };
-            // Issue order = event order of two softmax groups running half a period apart:
-            //   S0(j+1) | PV1(j-1) | S1(j+1) | PV0(j)     (the ncu capture of the first attn4 showed the groups
-            //   waiting ~25 % of their time for PV(j-1), queued behind both S(j+1), profiles/r01_ncu_attn4.txt)
-            if (p.order == 2) {
-                // independent pipeline per query tile: this thread only drives tile 0 (warp 2 drives tile 1)
-                for (int j = 0; j < nt; ++j) {
-                    if (j + 1 < nt) {
-                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
-                        next_s(0, j);
-                    }
-                    issue_pv(0, j);
-                    umma_commit(&kv_empty[j % A4_KV_STAGES]);
+            // independent pipeline per query tile: this thread only drives tile 0 (warp 2 drives tile 1)
+            for (int j = 0; j < nt; ++j) {
+                if (j + 1 < nt) {
+                    mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
+                    next_s(0, j);
                 }
-            } else             if (p.order == 1) {
-                for (int j = 0; j < nt; ++j) {
-                    const bool more = (j + 1 < nt);
-                    if (more) {
-                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
-                        next_s(0, j);
-                    }
-                    if (j > 0) {
-                        if (ntq > 1) issue_pv(1, j - 1);
-                        umma_commit(&kv_empty[(j - 1) % A4_KV_STAGES]);
-                    }
-                    if (more && ntq > 1) next_s(1, j);
-                    issue_pv(0, j);
-                }
-                if (ntq > 1) issue_pv(1, nt - 1);
-                umma_commit(&kv_empty[(nt - 1) % A4_KV_STAGES]);
-            } else {
-                for (int j = 0; j < nt; ++j) {
-                    if (j + 1 < nt) {
-                        mbar_wait(&kv_full[(j + 1) % A4_KV_STAGES], ((j + 1) / A4_KV_STAGES) & 1);
-                        for (int t = 0; t < ntq; ++t) next_s(t, j);
-                    }
-                    for (int t = 0; t < ntq; ++t) issue_pv(t, j);
-                    umma_commit(&kv_empty[j % A4_KV_STAGES]);
-                }
+                issue_pv(0, j);
+                umma_commit(&kv_empty[j % A4_KV_STAGES]);
             }
         }
     } else if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp == 2 && lane == 0 && p.order == 2 && ntq > 1) {
+        if (warp == 2 && lane == 0 && ntq > 1) {
             // second MMA-issuing thread: query tile 1
             constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, 0, 1);
@@ -249,7 +198,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 umma_commit(&kv_empty[j % A4_KV_STAGES]);
             }
         }
-    } else if constexpr (SPLIT != 0) {
+    } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int t = (warp - 4) >> 3;                   // query tile
         const int half = ((warp - 4) >> 2) & 1;          // score columns [64*half, +64) of every KV tile, O columns [32*half, +32)
@@ -311,16 +260,10 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int e = 0; e < 32; ++e) {
                     const int i = e * 2;
                     const uint64_t x01 = f2_fma(f2_pack_bits(v[i], v[i + 1]), sl2_2, negm_2);
-                    uint64_t p01;
-                    if (poly_slot<POLY_EVERY>(e)) {
-                        p01 = ex2_poly2(x01);
-                    } else {
-                        float x0, x1;
-                        f2_unpack(x01, x0, x1);
-                        p01 = f2_pack(ex2_approx(x0), ex2_approx(x1));
-                    }
-                    float p0, p1;
-                    f2_unpack(p01, p0, p1);
+                    float x0, x1;
+                    f2_unpack(x01, x0, x1);
+                    const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                    const uint64_t p01 = f2_pack(p0, p1);
                     pk[e] = pack_half2(p0, p1);
                     if (e & 1) l1 = f2_add(l1, p01);
                     else l0 = f2_add(l0, p01);
@@ -373,161 +316,6 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     w.z = pack_half2(__uint_as_float(o[u * 8 + 4]) * inv, __uint_as_float(o[u * 8 + 5]) * inv);
                     w.w = pack_half2(__uint_as_float(o[u * 8 + 6]) * inv, __uint_as_float(o[u * 8 + 7]) * inv);
                     reinterpret_cast<uint4*>(op)[u] = w;
-                }
-            }
-            tc_fence_before();
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        const int t = (warp - 4) >> 2;                   // query tile of this warpgroup
-        if (t < ntq) {
-            const int quad = warp & 3;
-            const int r = quad * 32 + lane;
-            const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-            const uint32_t t_s = tmem_base + t * 128 + lane_off;
-            const uint32_t t_o = tmem_base + 256 + t * 64 + lane_off;
-            const uint32_t t_p = tmem_base + 384 + t * 64 + lane_off;
-            const float sl2 = p.scale_log2;
-            float m_used = 0.f, l_run = 0.f;
-            const bool pingpong = (ntq == 2) && p.pingpong != 0;
-
-            // One KV tile of the online softmax.  TAIL is a compile-time tag: with a run-time `tail` flag ptxas
-            // if-converted the masking into an ISETP + SEL (+ VIADD) per element on EVERY tile -- 386 of the ~1300
-            // instructions per row and tile (SASS count), on warps that are issue-bound.
-            auto kv_tile = [&](const int j, auto tail_tag) {
-                constexpr bool tail = decltype(tail_tag)::value;
-                const int kbase = j * 128;
-                mbar_wait(&s_full[t], j & 1);
-                tc_fence_after();
-                uint32_t v[128];
-                tmem_ld32(t_s, v);
-                tmem_ld32(t_s + 32, v + 32);
-                tmem_ld32(t_s + 64, v + 64);
-                tmem_ld32(t_s + 96, v + 96);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&s_free[t]);                 // S_t may be overwritten by S_t(j+1)
-
-                float mx = -INFINITY;
-                if (tail) {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i)
-                        if (kbase + i >= p.Nk) v[i] = 0xff800000u;      // -inf
-                }
-                {
-                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
-#pragma unroll
-                    for (int i = 0; i < 128; i += 8) {
-                        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-                        m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
-                        m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-                    }
-                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                }
-                const float mc = mx * sl2;
-                float factor = 1.f;
-                bool need = false;
-                if (j == 0) {
-                    m_used = mc;
-                } else if (mc > m_used + 8.0f) {
-                    factor = ex2_approx(m_used - mc);
-                    m_used = mc;
-                    need = true;
-                }
-                // all exponentials first (registers only), THEN wait for PV(j-1): the ncu capture of the first attn4
-                // showed the softmax groups stalled ~25 % of their time on pv_done with the wait placed before the exps
-                // packed fp32x2 arithmetic (FFMA2 / FADD2): the softmax warps are issue-bound, every pair of
-                // probabilities costs one scale-and-shift, one row-sum add and one fp16 pack instead of two each
-                uint64_t l0 = 0ull, l1 = 0ull, l2 = 0ull, l3 = 0ull;
-                uint32_t pk[64];
-                const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(-m_used, -m_used);
-                // Exp-phase ping-pong.  Both query tiles start together, so without this the two softmax groups run in
-                // lock-step: both queue on the 16-lane MUFU for ~1500 clk, then both sit in the MUFU-free part of the
-                // iteration (S wait, TMEM load, row max, P store) -- ncu: XU pipe 55 % busy, tensor 36 %.  Taking turns
-                // puts one group's exponentials under the other group's load / max / store phase.
-                if (pingpong) mbar_wait(&turn[t], t == 0 ? ((j & 1) ^ 1) : (j & 1));
-#pragma unroll
-                for (int e = 0; e < 64; ++e) {
-                    const int i = e * 2;
-                    const uint64_t x01 = f2_fma(f2_pack_bits(v[i], v[i + 1]), sl2_2, negm_2);
-                    uint64_t p01;
-                    if (POLY_EVERY == 16) {
-                        float x0, x1;
-                        f2_unpack(x01, x0, x1);
-                        const uint32_t xh = pack_half2(x0, x1);
-                        uint32_t ph;
-                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
-                        const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&ph));
-                        p01 = f2_pack(pf.x, pf.y);
-                    } else if (poly_slot<POLY_EVERY>(e)) {
-                        p01 = ex2_poly2(x01);
-                    } else {
-                        float x0, x1;
-                        f2_unpack(x01, x0, x1);
-                        p01 = f2_pack(ex2_approx(x0), ex2_approx(x1));
-                    }
-                    float p0, p1;
-                    f2_unpack(p01, p0, p1);
-                    pk[e] = pack_half2(p0, p1);
-                    if ((e & 3) == 0) l0 = f2_add(l0, p01);
-                    else if ((e & 3) == 1) l1 = f2_add(l1, p01);
-                    else if ((e & 3) == 2) l2 = f2_add(l2, p01);
-                    else l3 = f2_add(l3, p01);
-                }
-                float l_lo, l_hi;
-                f2_unpack(f2_add(f2_add(l0, l1), f2_add(l2, l3)), l_lo, l_hi);
-                if (pingpong) mbar_arrive(&turn[1 - t]);
-                const float l_part = l_lo + l_hi;
-                if (j > 0) {
-                    mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, need)) {
-                        uint32_t o[32];
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            tmem_ld32(t_o + c * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                            tmem_st32(t_o + c * 32, o);
-                        }
-                        tmem_st_wait();
-                        l_run *= factor;
-                    }
-                }
-                tmem_st32(t_p, pk);
-                tmem_st32(t_p + 32, pk + 32);
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&p_full[t]);
-                l_run += l_part;
-            };
-#pragma unroll 1
-            for (int j = 0; j < nt - 1; ++j) kv_tile(j, TagFalse{});
-            if (p.Nk & 127) kv_tile(nt - 1, TagTrue{});
-            else kv_tile(nt - 1, TagFalse{});
-            // epilogue: O / l -> fp16
-            mbar_wait(&pv_done[t], (nt - 1) & 1);
-            tc_fence_after();
-            const int q = q0 + t * 128 + r;
-            const float inv = 1.0f / l_run;
-            __half* op = p.out + ((long long)batch * p.Nq + q) * p.ldo + head * 64;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld32(t_o + c * 32, o);
-                tmem_ld_wait();
-                if (q < p.Nq) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 w;
-                        w.x = pack_half2(__uint_as_float(o[u * 8 + 0]) * inv, __uint_as_float(o[u * 8 + 1]) * inv);
-                        w.y = pack_half2(__uint_as_float(o[u * 8 + 2]) * inv, __uint_as_float(o[u * 8 + 3]) * inv);
-                        w.z = pack_half2(__uint_as_float(o[u * 8 + 4]) * inv, __uint_as_float(o[u * 8 + 5]) * inv);
-                        w.w = pack_half2(__uint_as_float(o[u * 8 + 6]) * inv, __uint_as_float(o[u * 8 + 7]) * inv);
-                        reinterpret_cast<uint4*>(op + c * 32)[u] = w;
-                    }
                 }
             }
             tc_fence_before();

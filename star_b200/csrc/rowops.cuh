@@ -695,86 +695,6 @@ qk_ln_rope_kernel(__half* __restrict__ qkv, long long ld, long long rows, int he
     *reinterpret_cast<uint4*>(ptr) = pack8(f);
 }
 
-// ------------------------------------------------------------------ temporal self-attention (unet_v2v.py:483-489)
-// qkv [R, ld] with q | k | v at column offsets 0 | Ci | 2Ci, rows ordered (b, t, p); one warp per (b, p, head),
-// lane = query frame; K/V of the T frames staged in smem; online softmax in fp32.
-constexpr int TA_WARPS = 4;
-constexpr int TA_MAXT = 64;
-__global__ void __launch_bounds__(TA_WARPS * 32)
-temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int B,
-                     int T, long long HW, int heads, int Ci, float scale) {
-    extern __shared__ uint4 ta_smem[];                // per warp: K [T][8] uint4, V [T][8] uint4
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * TA_WARPS + warp;      // over (b, p, head), head fastest
-    const long long nitems = (long long)B * HW * heads;
-    if (item >= nitems) return;
-    const int head = (int)(item % heads);
-    const long long p = (item / heads) % HW;
-    const int b = (int)(item / (heads * HW));
-    uint4* ks = ta_smem + (size_t)warp * 2 * T * 8;
-    uint4* vs = ks + T * 8;
-    const long long row0 = (long long)b * T * HW + p;            // row of frame 0
-    for (int i = lane; i < T * 8; i += 32) {
-        const int t = i >> 3, ch = i & 7;
-        const __half* base = qkv + (row0 + (long long)t * HW) * ld + head * 64 + ch * 8;
-        ks[i] = __ldg(reinterpret_cast<const uint4*>(base + Ci));
-        vs[i] = __ldg(reinterpret_cast<const uint4*>(base + 2 * Ci));
-    }
-    __syncwarp();
-    const float sl2 = scale * 1.4426950408889634f;
-    for (int tq = lane; tq < T; tq += 32) {
-        uint4 qv[8];
-        const __half* qb = qkv + (row0 + (long long)tq * HW) * ld + head * 64;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) qv[c] = __ldg(reinterpret_cast<const uint4*>(qb + c * 8));
-        float o[64];
-#pragma unroll
-        for (int d = 0; d < 64; ++d) o[d] = 0.f;
-        float m = -INFINITY, l = 0.f;
-        for (int s = 0; s < T; ++s) {
-            float dot = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 kk = ks[s * 8 + c];
-                const __half2* qh = reinterpret_cast<const __half2*>(&qv[c]);
-                const __half2* kh = reinterpret_cast<const __half2*>(&kk);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 a = __half22float2(qh[e]), bb = __half22float2(kh[e]);
-                    dot = fmaf(a.x, bb.x, dot);
-                    dot = fmaf(a.y, bb.y, dot);
-                }
-            }
-            const float sc = dot * sl2;
-            const float m_new = fmaxf(m, sc);
-            const float alpha = exp2f(m - m_new);
-            const float pr = exp2f(sc - m_new);
-            l = l * alpha + pr;
-            m = m_new;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 vv = vs[s * 8 + c];
-                const __half2* vh = reinterpret_cast<const __half2*>(&vv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 a = __half22float2(vh[e]);
-                    o[c * 8 + e * 2] = fmaf(o[c * 8 + e * 2], alpha, pr * a.x);
-                    o[c * 8 + e * 2 + 1] = fmaf(o[c * 8 + e * 2 + 1], alpha, pr * a.y);
-                }
-            }
-        }
-        const float inv = 1.f / l;
-        __half* ob = out + (row0 + (long long)tq * HW) * ldo + head * 64;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = o[c * 8 + j] * inv;
-            *reinterpret_cast<uint4*>(ob + c * 8) = pack8(y);
-        }
-    }
-}
-
 // ------------------------------------------------------------------ elementwise / copies
 // out[R, Ca+Cb] = [ a | b (+ c) ]        decoder skip concat with the control residual (unet_v2v.py:1792)
 __global__ void concat_add_kernel(const __half* __restrict__ a, int Ca, const __half* __restrict__ b,

@@ -13,14 +13,11 @@
 
 #include "../../include/star_sm100.h"
 #include "attn.cuh"
-#include "attn2.cuh"
-#include "attn3.cuh"
 #include "attn4.cuh"
 #include "rowops.cuh"
 #include "tattn2.cuh"
 #include "tapgemm.cuh"
 #include "tapgemm2.cuh"
-#include "tapgemm2_pair.cuh"
 
 using namespace star;
 
@@ -28,24 +25,20 @@ namespace {
 
 thread_local std::string g_err;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-int g_num_sms = 148;
-int g_tattn_impl = 0;  // 1 = FMA-pipe temporal attention (debug override STAR_TATTN_IMPL)
-int g_gemm_impl = 0;   // 1 = force the non-persistent tap-GEMM (debug override STAR_GEMM_IMPL)
-int g_gemm_stages = 0; // cap on the tapgemm2 operand ring depth (debug override STAR_GEMM_STAGES)
-int g_gemm_wide_waste_longk = 25;   // ... and for reductions >= 1920 (N = 640 as 3 x 256: +16 % on the 640-channel convs)
-int g_gemm_wide_waste = 10;   // largest padding (percent of N) accepted for the 128x256 tiles (STAR_GEMM_WIDE_WASTE)
-int g_gemm_wide_mink = 256;   // smallest reduction length that takes the 128x256 tiles (STAR_GEMM_WIDE_MINK)
-int g_ln_impl = 0;         // 1 = one-row-per-warp LayerNorm for every width (debug override STAR_LN_IMPL)
-int g_gemm_pair = 0;       // 1: experimental CTA-pair (cta_group::2) tiles for the N = k*160 layers, 2: also BN = 128 (STAR_GEMM_PAIR)
-int g_gn_impl = 0;         // 1 = first-generation GroupNorm kernels (debug override STAR_GN_IMPL)
-int g_gemm_bn256 = 1;     // 128x256 persistent tiles where N % 256 == 0 (debug override STAR_GEMM_BN256=0)
-int g_attn_pingpong = 1;  // attn4 exp-phase ping-pong between the two softmax groups (debug override STAR_ATTN_PINGPONG)
-int g_attn_order = 2;  // attn4 MMA issue order (debug override STAR_ATTN_ORDER)
-int g_gemm_flags = 0;  // extra tap-GEMM flags OR-ed in (debug override STAR_GEMM_FLAGS, e.g. 4 = libdevice erff)
-int g_attn_impl = 0;   // 0 auto (attn3 for multi-tile problems, attn1 otherwise); 1/2/3 force a generation (debug: STAR_ATTN_IMPL)
-int g_attn_poly = 4;   // every n-th exponential pair on the FMA pipes (debug override STAR_ATTN_POLY: 0,2,3,4)
-bool g_attn_poly_set = false;   // the row-split kernel defaults to 0 (all MUFU), the thread-per-row kernels to 4
+constexpr int STAR_MAX_DEVICES = 64;
+int g_sms[STAR_MAX_DEVICES] = {0};            // SM count per initialised device (0 = star_init not called for it)
+// Tile-shape rules of the tap-GEMM dispatch (measured: profiles/r01_kbench_wide_tiles.log); constants, not switches.
+constexpr int kWideWastePct = 10;             // largest padding (percent of N) accepted for the 128x256 tiles ...
+constexpr int kWideWasteLongKPct = 25;        // ... and for reductions >= 1920 (N = 640 as 3 x 256: +16 % on the 640-channel convs)
+constexpr int kWideMinK = 256;                // smallest reduction length that takes the 128x256 tiles
 std::atomic<long long> g_launches{0};
+
+// SM count of the CURRENT device (kernels are launched on the caller's current device / stream)
+inline int num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < STAR_MAX_DEVICES && g_sms[dev] > 0) return g_sms[dev];
+    return 148;
+}
 
 int fail(const char* fmt, ...) {
     char buf[1024];
@@ -57,8 +50,12 @@ int fail(const char* fmt, ...) {
     return 1;
 }
 
-#define STAR_CHECK_INIT() \
-    if (!g_encode) return fail("star_init() has not been called (or failed)")
+#define STAR_CHECK_INIT()                                                                                        \
+    do {                                                                                                         \
+        int dev_ = -1;                                                                                           \
+        if (!g_encode || cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= STAR_MAX_DEVICES || !g_sms[dev_]) \
+            return fail("star_init(%d) has not been called for the current device (or failed)", dev_);           \
+    } while (0)
 #define STAR_CUDA(x)                                                                        \
     do {                                                                                    \
         cudaError_t e_ = (x);                                                               \
@@ -97,7 +94,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
 
 inline int grid_for(long long n, int block, int cap_mult = 32) {
     long long g = (n + block - 1) / block;
-    return (int)std::max(1ll, std::min(g, (long long)g_num_sms * cap_mult));
+    return (int)std::max(1ll, std::min(g, (long long)num_sms() * cap_mult));
 }
 
 // ------------------------------------------------------------------ tap-GEMM launcher
@@ -184,7 +181,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     p.K = d.K;
     p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
     p.N = d.N;
-    p.flags = d.flags | g_gemm_flags;
+    p.flags = d.flags;
     p.bias = (const __half*)d.bias;
     p.rowvec = (const __half*)d.rowvec;
     p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
@@ -229,99 +226,10 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     } else {
         tr = to;
     }
-    const int grid = (int)std::min<long long>(total, g_num_sms);
+    const int grid = (int)std::min<long long>(total, num_sms());
     ex.stages = TapGemm2Smem<BN>::stages(d.residual != nullptr);
-    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
     tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
-    return 0;
-}
-
-// experimental CTA-pair configuration (tapgemm2_pair.cuh), reached only with STAR_GEMM_PAIR
-template <int BN>
-int launch_tapgemm2_pair_bn(const TapDesc& d, cudaStream_t st) {
-    TapGemmParams p;
-    memset(&p, 0, sizeof(p));
-    long long m_tiles = 1;
-    int box_rows = 1;
-    for (int i = 0; i < 4; ++i) {
-        p.on[i] = d.on[i];
-        p.box[i] = d.box[i];
-        p.tiles[i] = (d.on[i] + d.box[i] - 1) / d.box[i];
-        m_tiles *= p.tiles[i];
-        box_rows *= d.box[i];
-    }
-    if (box_rows > TG_BM) return fail("tapgemm2: box has %d rows (> %d)", box_rows, TG_BM);
-    p.box_rows = box_rows;
-    p.ntaps = d.ntaps;
-    memcpy(p.tap, d.tap, sizeof(p.tap));
-    p.K = d.K;
-    p.k_chunks = (d.K + TG_BK - 1) / TG_BK;
-    p.N = d.N;
-    p.flags = d.flags | g_gemm_flags;
-    p.bias = (const __half*)d.bias;
-    p.rowvec = (const __half*)d.rowvec;
-    p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
-    p.residual = (const __half*)d.residual;
-    p.colscale = (const __half*)d.colscale;
-    p.res_ld = d.ldres;
-    p.out = (__half*)d.out;
-    p.out_ld = d.ldo;
-    const bool geglu = d.flags & TG_GEGLU;
-    const int n_per_tile = geglu ? BN / 2 : BN;
-    TapGemm2PairExtra ex;
-    ex.n_tiles = (d.N + n_per_tile - 1) / n_per_tile;
-    ex.m_tiles = (int)m_tiles;
-    const long long total = (m_tiles + 1) / 2 * ex.n_tiles;                   // 256-row pair tiles
-    if (total > 0x7fffffffll) return fail("tapgemm2: too many tiles");
-    ex.num_tiles = (int)total;
-
-    CUtensorMap ta, tw, to, tr;
-    unsigned abox[5] = {TG_BK, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
-    if (make_tmap(&ta, d.A, 5, d.adim, d.astr, abox)) return 1;
-    const unsigned long long wrows = geglu ? 2ull * d.N : (unsigned long long)d.N;
-    unsigned long long wdim[2] = {(unsigned long long)d.ntaps * d.K, wrows};
-    unsigned long long wstr[2] = {1, (unsigned long long)d.ntaps * d.K};
-    unsigned wbox[2] = {TG_BK, (unsigned)(BN / 2)};                                  // each CTA loads half a weight tile
-    if (make_tmap(&tw, d.W, 2, wdim, wstr, wbox)) return 1;
-    // output / residual: (N, n1..n4) with row pitch ld; 32-column boxes, SWIZZLE_64B staging tiles
-    unsigned obox[5] = {32, (unsigned)d.box[0], (unsigned)d.box[1], (unsigned)d.box[2], (unsigned)d.box[3]};
-    unsigned long long odim[5] = {(unsigned long long)d.N, (unsigned long long)d.on[0], (unsigned long long)d.on[1],
-                                  (unsigned long long)d.on[2], (unsigned long long)d.on[3]};
-    auto strides = [&](long long ld, unsigned long long* s) {
-        s[0] = 1;
-        s[1] = (unsigned long long)ld;
-        s[2] = s[1] * d.on[0];
-        s[3] = s[2] * d.on[1];
-        s[4] = s[3] * d.on[2];
-    };
-    unsigned long long ostr[5], rstr[5];
-    strides(d.ldo, ostr);
-    if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (d.residual && TapGemm2PairSmem<BN>::RES_TMA) {
-        strides(d.ldres, rstr);
-        if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    } else {
-        tr = to;
-    }
-    ex.stages = TapGemm2PairSmem<BN>::stages(d.residual != nullptr);
-    if (g_gemm_stages > 1 && g_gemm_stages < ex.stages) ex.stages = g_gemm_stages;
-    // clusters of two CTAs (one TPC): an even grid, at most one cluster per pair tile
-    const int grid = (int)std::min<long long>(2 * total, (long long)(g_num_sms & ~1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TG2_THREADS);
-    cfg.dynamicSmemBytes = TapGemm2PairSmem<BN>::total(d.residual != nullptr);
-    cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    STAR_CUDA(cudaLaunchKernelEx(&cfg, tapgemm2_pair_kernel<BN>, ta, tw, to, tr, p, ex));
-    STAR_LAUNCH_CHECK("tapgemm2_pair");
     return 0;
 }
 
@@ -341,16 +249,13 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
     // profiles/r01_kbench_wide_tiles.log) (N = 960, 1280, 1920, 2560, 3840, ...; GEGLU: 128 outputs per tile).
     const int wide_n = geglu ? 128 : 256;
     const long long padded = ((long long)d.N + wide_n - 1) / wide_n * wide_n;
-    const bool wide = aligned && (padded * 100 <= (long long)d.N * (100 + ((long long)d.ntaps * d.K >= 1920 ? g_gemm_wide_waste_longk : g_gemm_wide_waste))) && ((long long)d.ntaps * d.K >= g_gemm_wide_mink) &&
-                      g_gemm_bn256 != 0 && !(geglu && g_gemm_bn256 == 2) && g_gemm_impl != 1;
+    const long long red = (long long)d.ntaps * d.K;
+    const bool wide = aligned && red >= kWideMinK &&
+                      padded * 100 <= (long long)d.N * (100 + (red >= 1920 ? kWideWasteLongKPct : kWideWastePct));
     if (wide) return launch_tapgemm2_bn<256>(d, st);
-    if (aligned && g_gemm_impl != 1 && !(long_k && g_gemm_impl != 2)) {
-        if (!geglu && d.N % 160 == 0 && d.N % 128 != 0)
-            return g_gemm_pair ? launch_tapgemm2_pair_bn<160>(d, st) : launch_tapgemm2_bn<160>(d, st);
-        return g_gemm_pair == 2 ? launch_tapgemm2_pair_bn<128>(d, st) : launch_tapgemm2_bn<128>(d, st);
-    }
-    if (!geglu && d.N % 160 == 0 && d.N % 128 != 0) return launch_tapgemm_bn<160>(d, st);
-    return launch_tapgemm_bn<128>(d, st);
+    const bool n160 = !geglu && d.N % 160 == 0 && d.N % 128 != 0;
+    if (aligned && !long_k) return n160 ? launch_tapgemm2_bn<160>(d, st) : launch_tapgemm2_bn<128>(d, st);
+    return n160 ? launch_tapgemm_bn<160>(d, st) : launch_tapgemm_bn<128>(d, st);
 }
 
 void best_box_2d(int H, int W, int* th, int* tw) {
@@ -375,12 +280,12 @@ int star_version(void) { return 100; }
 const char* star_last_error(void) { return g_err.c_str(); }
 long long star_launch_count(void) { return g_launches.load(); }
 
-int star_init(int device) {
-    STAR_CUDA(cudaSetDevice(device));
+// Per-device initialisation: checks the architecture, records the SM count and raises the dynamic shared-memory limit of
+// every kernel ON THAT DEVICE (function attributes are per device).  The caller's current device is restored.
+static int star_init_on_current(int device) {
     cudaDeviceProp prop;
     STAR_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail("libstar_sm100 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
-    g_num_sms = prop.multiProcessorCount;
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
@@ -388,52 +293,33 @@ int star_init(int device) {
         if (!fn || qr != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
         g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<128>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmSmem<160>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmemT<false>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmemT<true>::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true))));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true))));
-    STAR_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true))));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA((cudaFuncSetAttribute(attn4_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL)));
-    STAR_CUDA((cudaFuncSetAttribute(attn4_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL)));
-    STAR_CUDA(cudaFuncSetAttribute(attn4_fwd_kernel<38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
-    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 16 * TA2_PITCH));
-    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 32 * TA2_PITCH));
-    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 48 * TA2_PITCH));
-    STAR_CUDA(cudaFuncSetAttribute(temporal_attn2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA2_WARPS * 3 * 64 * TA2_PITCH));
-    if (const char* e = getenv("STAR_TATTN_IMPL")) g_tattn_impl = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_IMPL")) g_gemm_impl = atoi(e);
-    if (const char* e = getenv("STAR_ATTN_IMPL")) g_attn_impl = atoi(e);
-    if (const char* e = getenv("STAR_ATTN_ORDER")) g_attn_order = atoi(e);
-    if (const char* e = getenv("STAR_ATTN_PINGPONG")) g_attn_pingpong = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_FLAGS")) g_gemm_flags = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_STAGES")) g_gemm_stages = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_BN256")) g_gemm_bn256 = atoi(e);
-    if (const char* e = getenv("STAR_GN_IMPL")) g_gn_impl = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_PAIR")) g_gemm_pair = atoi(e);
-    if (g_gemm_pair) {            // the experimental pair kernels are not touched at all unless asked for
-        STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<160>::total(false), TapGemm2PairSmem<160>::total(true))));
-        STAR_CUDA(cudaFuncSetAttribute(tapgemm2_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(TapGemm2PairSmem<128>::total(false), TapGemm2PairSmem<128>::total(true))));
-    }
-    if (const char* e = getenv("STAR_LN_IMPL")) g_ln_impl = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_WIDE_MINK")) g_gemm_wide_mink = atoi(e);
-    if (const char* e = getenv("STAR_GEMM_WIDE_WASTE")) g_gemm_wide_waste = atoi(e);
-    if (const char* e = getenv("STAR_ATTN_POLY")) { g_attn_poly = atoi(e); g_attn_poly_set = true; }
-    STAR_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   TA_WARPS * 2 * TA_MAXT * 128));
+#define STAR_SMEM_ATTR(kernel, bytes) STAR_CUDA((cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))))
+    STAR_SMEM_ATTR(tapgemm_kernel<128>, TapGemmSmem<128>::TOTAL);
+    STAR_SMEM_ATTR(tapgemm_kernel<160>, TapGemmSmem<160>::TOTAL);
+    STAR_SMEM_ATTR(tapgemm2_kernel<128>, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true)));
+    STAR_SMEM_ATTR(tapgemm2_kernel<160>, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true)));
+    STAR_SMEM_ATTR(tapgemm2_kernel<256>, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true)));
+    STAR_SMEM_ATTR(attn_fwd_kernel<false>, AttnSmemT<false>::TOTAL);
+    STAR_SMEM_ATTR(attn_fwd_kernel<true>, AttnSmemT<true>::TOTAL);
+    STAR_SMEM_ATTR(attn4_fwd_kernel, Attn4Smem::TOTAL);
+    STAR_SMEM_ATTR(temporal_attn2_kernel<16>, TA2_WARPS * 3 * 16 * TA2_PITCH);
+    STAR_SMEM_ATTR(temporal_attn2_kernel<32>, TA2_WARPS * 3 * 32 * TA2_PITCH);
+    STAR_SMEM_ATTR(temporal_attn2_kernel<48>, TA2_WARPS * 3 * 48 * TA2_PITCH);
+    STAR_SMEM_ATTR(temporal_attn2_kernel<64>, TA2_WARPS * 3 * 64 * TA2_PITCH);
+    STAR_SMEM_ATTR(softmax_rows_kernel, 200 * 1024);
+#undef STAR_SMEM_ATTR
+    g_sms[device] = prop.multiProcessorCount;
     return 0;
+}
+
+int star_init(int device) {
+    if (device < 0 || device >= STAR_MAX_DEVICES) return fail("star_init: device index %d out of range", device);
+    int prev = -1;
+    STAR_CUDA(cudaGetDevice(&prev));
+    if (prev != device) STAR_CUDA(cudaSetDevice(device));
+    const int rc = star_init_on_current(device);
+    if (prev != device && prev >= 0) cudaSetDevice(prev);          // never change the caller's current device
+    return rc;
 }
 
 int star_linear(const void* A, long long lda, const void* W, const void* bias, const void* rowvec,
@@ -606,83 +492,34 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
-    p.order = g_attn_order;
-    p.pingpong = g_attn_pingpong;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
-    const bool multi = Nk > AT_BKV && Nq > AT_BQ;
-    // Default for the multi-tile case: the row-split kernel with every exponential on the MUFU.  In-step A/B on the full
-    // model (profiles/r01_bench_ab_attention.log): split/poly0 36.3 ms per finest-level launch, split/poly4 38.1,
-    // thread-per-row/poly4 39.2 (all at ~1.70 GHz under the power cap).
-    if (g_attn_impl == 5 || (g_attn_impl == 0 && multi)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    // Multi-tile problems (spatial self-attention): two 128-row query tiles per CTA, row-split softmax, every exponential on
+    // the MUFU (in-step A/B on the full model: profiles/r01_bench_ab_attention.log).  Single-KV-tile problems (text
+    // cross-attention, tiny latents): the one-tile kernel, two CTAs per SM.
+    if (Nk > AT_BKV && Nq > AT_BQ) {
         dim3 grid((Nq + 255) / 256, heads, batch);
-        cudaStream_t st = (cudaStream_t)stream;
-        if (!g_attn_poly_set || g_attn_poly == 0) attn4_fwd_kernel<0, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
-        else attn4_fwd_kernel<4, 1><<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
-        STAR_LAUNCH_CHECK("attn4_split_fwd");
-        return 0;
-    }
-    if (g_attn_impl == 4) {
-        dim3 grid((Nq + 255) / 256, heads, batch);
-        cudaStream_t st = (cudaStream_t)stream;
-        switch (g_attn_poly) {
-            case 4: attn4_fwd_kernel<4><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 3: attn4_fwd_kernel<3><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 2: attn4_fwd_kernel<2><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 38: attn4_fwd_kernel<38><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            default: attn4_fwd_kernel<0><<<grid, A4_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-        }
+        attn4_fwd_kernel<<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
         STAR_LAUNCH_CHECK("attn4_fwd");
         return 0;
     }
-    if (g_attn_impl == 3) {
-        dim3 grid((Nq + 255) / 256, heads, batch);
-        cudaStream_t st = (cudaStream_t)stream;
-        switch (g_attn_poly) {
-            case 4: attn3_fwd_kernel<4><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 3: attn3_fwd_kernel<3><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            default: attn3_fwd_kernel<0><<<grid, A3_THREADS, Attn3Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-        }
-        STAR_LAUNCH_CHECK("attn3_fwd");
-        return 0;
-    }
-    const bool two_tile = g_attn_impl == 2;
-    if (two_tile) {
-        dim3 grid((Nq + 255) / 256, heads, batch);
-        cudaStream_t st = (cudaStream_t)stream;
-        switch (g_attn_poly) {
-            case 0: attn2_fwd_kernel<0><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 2: attn2_fwd_kernel<2><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            case 3: attn2_fwd_kernel<3><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-            default: attn2_fwd_kernel<4><<<grid, A2_THREADS, Attn2Smem::TOTAL, st>>>(tq, tk, tv, p); break;
-        }
-        STAR_LAUNCH_CHECK("attn2_fwd");
-        return 0;
-    }
     dim3 grid((Nq + AT_BQ - 1) / AT_BQ, heads, batch);
-    if (Nk <= AT_BKV && g_attn_impl != 1)
-        attn_fwd_kernel<true><<<grid, AT_THREADS, AttnSmemT<true>::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    else
-        attn_fwd_kernel<false><<<grid, AT_THREADS, AttnSmemT<false>::TOTAL, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    if (Nk <= AT_BKV) attn_fwd_kernel<true><<<grid, AT_THREADS, AttnSmemT<true>::TOTAL, st>>>(tq, tk, tv, p);
+    else attn_fwd_kernel<false><<<grid, AT_THREADS, AttnSmemT<false>::TOTAL, st>>>(tq, tk, tv, p);
     STAR_LAUNCH_CHECK("attn_fwd");
     return 0;
 }
 
 int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,
                             int heads, int Ci, float scale, void* stream) {
-    if (T > TA_MAXT || T < 1) return fail("star_temporal_attention: T=%d outside [1, %d]", T, TA_MAXT);
+    STAR_CHECK_INIT();
+    if (T > TA2_MAXT || T < 1) return fail("star_temporal_attention: T=%d outside [1, %d]", T, TA2_MAXT);
     if (ld % 8 || ldo % 8 || Ci % 8) return fail("star_temporal_attention: ld/ldo/Ci must be multiples of 8");
     if ((reinterpret_cast<uintptr_t>(QKV) | reinterpret_cast<uintptr_t>(O)) % 16) return fail("star_temporal_attention: pointers must be 16-byte aligned");
     const long long items = (long long)B * HW * heads;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_tattn_impl == 1) {
-        const long long blocks = (items + TA_WARPS - 1) / TA_WARPS;
-        temporal_attn_kernel<<<(unsigned)blocks, TA_WARPS * 32, TA_WARPS * 2 * T * 128, st>>>(
-            (const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale);
-        STAR_LAUNCH_CHECK("temporal_attn");
-        return 0;
-    }
     const int tp = (T + 15) / 16 * 16;
-    const unsigned grid = (unsigned)std::min<long long>((items + TA2_WARPS - 1) / TA2_WARPS, (long long)g_num_sms * 2);
+    const unsigned grid = (unsigned)std::min<long long>((items + TA2_WARPS - 1) / TA2_WARPS, (long long)num_sms() * 2);
     const size_t smem = (size_t)TA2_WARPS * 3 * tp * TA2_PITCH;
 #define STAR_TA2(TPV) temporal_attn2_kernel<TPV><<<grid, TA2_WARPS * 32, smem, st>>>((const __half*)QKV, ld, (__half*)O, ldo, B, T, HW, heads, Ci, scale)
     switch (tp) {
@@ -710,14 +547,14 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
     float* ab = (float*)((char*)workspace + (size_t)nsamples * 32 * 2 * 8);
     STAR_CUDA(cudaMemsetAsync(stats, 0, (size_t)nsamples * 32 * 2 * 8, st));
     const long long total_rows = rows_per_sample * nsamples;
-    if (C / 8 <= GN2_THREADS && g_gn_impl != 1) {
+    if (C / 8 <= GN2_THREADS) {
         // persistent CTAs over contiguous slab ranges: statistics / (a, b) stay in registers across slabs
         Gn2Range rg;
         rg.slabs_per_sample = (rows_per_sample + GN2_SLAB - 1) / GN2_SLAB;
         rg.total_slabs = rg.slabs_per_sample * nsamples;
         const int lanes2 = GN2_THREADS / (C / 8);
         const size_t smem2 = (size_t)lanes2 * C * 2 * sizeof(float);
-        const unsigned grid2 = (unsigned)std::min<long long>(rg.total_slabs, (long long)g_num_sms * 8);
+        const unsigned grid2 = (unsigned)std::min<long long>(rg.total_slabs, (long long)num_sms() * 8);
         gn_stats2_kernel<<<grid2, GN2_THREADS, smem2, st>>>((const __half*)X, stats, rows_per_sample, C, rg);
         STAR_LAUNCH_CHECK("gn_stats2");
         gn_finalize_kernel<<<nsamples, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows_per_sample, C, eps);
@@ -742,10 +579,10 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
 int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,
                    int gate_mode, const void* gate, float w0, float w1, void* stream) {
     if (C % 8 || C / 8 > 32 * 12) return fail("star_layernorm: unsupported C=%d", C);
-    if ((C == 320 || C == 640) && g_ln_impl != 1) {
+    if (C == 320 || C == 640) {
         const int rpw = C == 320 ? 4 : 2;
         const long long groups = (rows + rpw - 1) / rpw;
-        const unsigned g2 = (unsigned)std::min<long long>((groups + 7) / 8, (long long)g_num_sms * 6);
+        const unsigned g2 = (unsigned)std::min<long long>((groups + 7) / 8, (long long)num_sms() * 6);
         if (C == 320)
             layernorm_sub_kernel<8><<<g2, 256, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma, (const __half*)beta,
                                                                           (__half*)out, rows, eps, gate_mode, (const __half*)gate, w0, w1);
@@ -757,7 +594,7 @@ int star_layernorm(const void* X, const void* gamma, const void* beta, void* out
     }
     const int wpb = 8;
     const long long want = (rows + wpb - 1) / wpb;
-    const unsigned grid = (unsigned)std::min<long long>(want, (long long)g_num_sms * 6);
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)num_sms() * 6);
     const int oct = (C / 8 + 31) / 32;
 #define STAR_LN_LAUNCH(N)                                                                                          \
     layernorm_kernel<N><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __half*)X, (const __half*)gamma,          \
@@ -777,7 +614,7 @@ int star_liem_spatial_gate(const void* X, const void* w98, void* mm_ws, void* ga
     if (C % 8) return fail("star_liem_spatial_gate: C must be a multiple of 8");
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)BT * H * W;
-    liem_reduce_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, (long long)g_num_sms * 8), 256, 0, st>>>((const __half*)X, (__half*)mm_ws, rows, C);
+    liem_reduce_kernel<<<(unsigned)std::min<long long>((rows + 7) / 8, (long long)num_sms() * 8), 256, 0, st>>>((const __half*)X, (__half*)mm_ws, rows, C);
     STAR_LAUNCH_CHECK("liem_reduce");
     liem_conv7_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __half*)mm_ws, (const __half*)w98, (__half*)gate,
                                                                        BT, H, W);
@@ -789,7 +626,7 @@ int star_row_gate(const void* X, void* out, long long rows, int C, int mode, con
                   void* stream) {
     if (C % 8) return fail("star_row_gate: C must be a multiple of 8");
     if (mode != 1 && mode != 2) return fail("star_row_gate: mode must be 1 (external gate) or 2 (temporal LIEM)");
-    const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, (long long)g_num_sms * 8);
+    const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, (long long)num_sms() * 8);
     row_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, rows, C, mode, (const __half*)gate, w0, w1);
     STAR_LAUNCH_CHECK("row_gate");
     return 0;
@@ -838,17 +675,13 @@ int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, 
 }
 
 int star_softmax_rows(void* S, long long ld, long long rows, int cols, void* stream) {
+    STAR_CHECK_INIT();
     if (rows <= 0) return 0;
     if (ld % 8 || reinterpret_cast<uintptr_t>(S) % 16) return fail("star_softmax_rows: rows must be 16-byte aligned (ld %% 8 == 0)");
     if (cols <= 0 || cols > ld) return fail("star_softmax_rows: need 0 < cols <= ld");
     const size_t smem = ((size_t)cols * 2 + 15) / 16 * 16;
     if (smem > 200 * 1024) return fail("star_softmax_rows: %d columns do not fit in shared memory", cols);
     if (rows > 0x7fffffffll) return fail("star_softmax_rows: too many rows");
-    static bool attr_set = false;
-    if (!attr_set) {
-        STAR_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     softmax_rows_kernel<<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>((__half*)S, ld, cols);
     STAR_LAUNCH_CHECK("softmax_rows");
     return 0;

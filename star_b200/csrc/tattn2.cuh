@@ -15,6 +15,7 @@
 namespace star {
 
 constexpr int TA2_WARPS = 8;
+constexpr int TA2_MAXT = 64;             // frames per chunk (the reference uses 32, stretched last chunk up to 40)
 constexpr int TA2_PITCH = 144;           // bytes per smem row (128 B of data + 16 B pad)
 
 STAR_DEVINL void cp_async16(uint32_t dst, const void* src) {

@@ -34,17 +34,26 @@ def trace_end():
 
 
 def _traced(fn):
+    """Every op runs with its first tensor's device current (kernels are launched on the CURRENT device and stream:
+    a model on cuda:1 must not launch on cuda:0 with foreign pointers), and is optionally timed."""
     import functools
+
+    def guarded(*args, **kw):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kw)
+        return fn(*args, **kw)
 
     @functools.wraps(fn)
     def wrapper(*args, **kw):
         if _trace is None:
-            return fn(*args, **kw)
+            return guarded(*args, **kw)
         sig = tuple(tuple(a.shape) if torch.is_tensor(a) else a for a in args
                     if torch.is_tensor(a) or isinstance(a, (int, float)))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out = fn(*args, **kw)
+        out = guarded(*args, **kw)
         b.record()
         _trace.append((fn.__name__, sig, a, b))
         return out

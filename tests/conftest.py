@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # GPU-side "fp32" references must be fp32: cuDNN convolutions default to TF32 (10-bit mantissa) and would be a
+    # weaker oracle than the kernels under test
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100) device")
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (build container only)")
 

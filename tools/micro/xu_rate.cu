@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk, int reps) {
                 asm volatile("fma.rn.ftz.f32x2 %0, %1, %1, %1;" : "=l"(y) : "l"(x));
                 asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(b[i]) : "l"(y));
             }
+            if (MODE == 6) asm volatile("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %0; ex2.approx.f16 lo, lo; mov.b32 %0, {lo, hi};}" : "+r"(h[i]));
+            if (MODE == 7) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
             if (MODE == 5) asm volatile("max.ftz.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b[i]), "f"(b[(i + 1) & 7]));
         }
     }
@@ -62,5 +64,7 @@ int main() {
     run<3>("MUFU.EX2 + F2FP interleaved", 2);
     run<4>("FFMA2 (fma.f32x2)", 1);
     run<5>("FMNMX3 (3-input max)", 1);
+    run<6>("MUFU.EX2.F16 (scalar half)", 1);
+    run<7>("ex2.approx.f16x2 (2 x MUFU.EX2.F16 + PRMT per instruction)", 1);
     return 0;
 }
