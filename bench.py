@@ -15,6 +15,11 @@ Metric (BASELINE.json): upscaled frames/sec, 4x 240p->960p I2VGen-XL, 32-frame c
     chunk, so the clip has 16(N+1) unique frames: that rate is config.unique_frames_per_s.
   * e2e: the same metric through VideoToVideo_sr.denoise_latents() from pinned HOST tensors, one
     1-step call per "step": H2D of latent + text embeddings and D2H of the result inside the timing.
+  * gpu_reference (N=1): the UNMODIFIED reference modules (.half() + autocast, xformers -> SDPA) timed on the same B200 on
+    the same shape in a child process (tools/ref_gpu.py; needs the staged tree oracle/_ref, see oracle/stage_reference.py):
+    the denominator of the north-star's ">= 8x the reference's single-GPU PyTorch frames/sec".
+  * config3 (N>=6): BASELINE config 3 -- a 72-frame clip = chunks 32/32/40 -- on the same ranks with the CFG-branch split
+    (6 active ranks, load imbalance 40/32), reported beside the weak-scaling line.
   * --impl reference: the oracle's CPU/fp32 restatement of the reference path (oracle/unet_ref.py,
     pinned against the real reference) timed on the host cores on a bounded sample.
 """
@@ -46,6 +51,7 @@ def parse():
     ap.add_argument("--lat-w", type=int, default=LAT_W)
     ap.add_argument("--frames", type=int, default=0, help="override clip length (default 32, or 16(N+1) for N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-on-this-GPU block (needs oracle/_ref)")
     ap.add_argument("--trace-out", default="", help="write the per-op time table of the timed region to this file")
     ap.add_argument("--no-vae", action="store_true", help="skip the (separately reported) VAE encode/decode legs")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; not a valid bench line)")
@@ -250,40 +256,83 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
-def time_vae(pipe, latent, F, H, W, dev, ms_per_step):
+def time_vae(pipe, latent, F, H, W, dev, ms_per_step, world=1, rank=0, barrier=None):
     """Temporal VAE around the denoise loop (ref video_to_video_model.py:141-161), synthetic weights: decode of the
-    F-frame clip as 3-frame windows and encode of F frames one by one, device-timed; plus frames/s of the whole
-    50-step pipeline with those legs included."""
+    F-frame clip as 3-frame windows and per-frame encode, device-timed; plus frames/s of the whole 50-step pipeline with
+    those legs included.  N>1: the pipeline's own sharding -- every rank decodes its share of the windows and encodes its
+    share of the frames, ONE all-gather of decoded frames / of latents (VideoToVideo_sr._decode_sharded, .test)."""
+    import torch.distributed as dist
     from star_b200.utils.synth import synth_tensor
     from star_b200.video_to_video.modules.temporal_vae import AutoencoderKLTemporalDecoder
+    from star_b200.video_to_video.video_to_video_model import _all_gather_varlen, _shard_bounds
     with torch.device("meta"):
         vae = AutoencoderKLTemporalDecoder()
     vae.load_state_dict({k: synth_tensor(k, v.shape, 0, dev) for k, v in vae.state_dict().items()}, assign=True)
     old, pipe.vae = pipe.vae, vae.eval().requires_grad_(False)
     try:
         z = latent[:, :, :F].float()
-        pix = torch.rand(1, min(F, 8), 3, 8 * H, 8 * W, device=dev) * 2 - 1          # encode is per frame: time 8, scale to F
+        bounds = _shard_bounds(F, world)
+        lo, hi = bounds[rank]
+        n_enc = min(hi - lo, 8) if world == 1 else hi - lo                  # N=1: time 8 frames, scale to F (encode is per frame)
+        pix = torch.rand(1, max(n_enc, 1), 3, 8 * H, 8 * W, device=dev) * 2 - 1
         pipe.vae_decode_chunk(z[:, :, :3], chunk_size=3)
         pipe.vae_encode(pix[:, :1])
-        torch.cuda.synchronize()
+        (barrier or torch.cuda.synchronize)()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        vid = pipe.vae_decode_chunk(z, chunk_size=3)
+        if world == 1:
+            vid = pipe.vae_decode_chunk(z, chunk_size=3)
+        else:
+            vid = pipe._decode_sharded(z, 3, (0, 8 * H, 0, 8 * W))
         ev[1].record()
-        pipe.vae_encode(pix)
+        lat = pipe.vae_encode(pix[:, :n_enc]) if n_enc else torch.zeros((1, 4, 0, H, W), device=dev)
+        if world > 1:
+            lat = _all_gather_varlen(lat.float(), [b - a for a, b in bounds], 2)
         ev[2].record()
-        torch.cuda.synchronize()
+        (barrier or torch.cuda.synchronize)()
         dec_ms = ev[0].elapsed_time(ev[1])
-        enc_ms = ev[1].elapsed_time(ev[2]) * F / pix.shape[1]
-        ok = bool(torch.isfinite(vid).all())
+        enc_ms = ev[1].elapsed_time(ev[2]) * (F / max(n_enc, 1) if world == 1 else 1.0)
+        if world > 1:
+            tt = torch.tensor([dec_ms, enc_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dec_ms, enc_ms = tt.tolist()
+        ok = bool(torch.isfinite(vid).all()) and vid.shape[0] == F
         denoise_s = SCHEDULE_STEPS * ms_per_step / 1e3
         return {"vae": "star_b200 AutoencoderKLTemporalDecoder (sm_100a kernels), synthetic weights, parity unpinned",
+                "sharding": "single GPU" if world == 1 else
+                            f"3-frame decode windows round-robin over {world} ranks + ONE all-gather of decoded frames; "
+                            f"per-frame encode of each rank's share + all-gather of latents",
+                "decode_ms_per_clip": dec_ms, "encode_ms_per_clip": enc_ms,
                 "decode_ms_per_frame": dec_ms / F, "encode_ms_per_frame": enc_ms / F, "decoded_finite": ok,
                 "frames_per_s_denoise_only": F / denoise_s,
                 "frames_per_s_denoise_decode": F / (denoise_s + dec_ms / 1e3),
                 "frames_per_s_encode_denoise_decode": F / (denoise_s + (dec_ms + enc_ms) / 1e3)}
     finally:
         pipe.vae = old
+
+
+def gpu_reference_block(H, W):
+    """the unmodified reference modules on this B200 (child process, after the product's memory is released)"""
+    staged = os.path.join(ROOT, "oracle", "_ref", "video_to_video", "modules", "unet_v2v.py")
+    recorded = os.path.join(ROOT, "profiles", "r02_ref_gpu_c2.json")
+    note = {"what": "reference ControlledV2VUNet().half() under torch.autocast('cuda', fp16), xformers.memory_efficient_attention -> "
+                    "F.scaled_dot_product_attention (xformers 0.0.21 has no sm_100 build); same weights / shape as `value`",
+            "recorded_run": "profiles/r02_ref_gpu_c2.json (2 244 ms per forward, 0.1426 frames/s; star 751 ms; parity at this shape)"
+            if os.path.isfile(recorded) else None}
+    if not (os.path.isfile(staged) or os.path.isfile("/root/reference/video_to_video/modules/unet_v2v.py")):
+        return dict(note, unavailable="reference tree not on this box (oracle/_ref is git-ignored; run `python -m oracle.stage_reference` "
+                                      "in the build container before shipping)")
+    out = os.path.join(ROOT, "gpurun_out", "bench_gpu_reference.json")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu.py"), "--no-star", "--no-fp32", "--iters", "3",
+                            "--shape", f"{CHUNK},{H},{W}", "--out", out], capture_output=True, text=True, timeout=420)
+        d = json.load(open(out))
+        ms = min(d["ref_fp16_ms_per_forward"])
+        return dict(note, ms_per_forward=ms, ms_per_step=2 * ms, value=CHUNK / (SCHEDULE_STEPS * 2 * ms / 1e3), unit="frames/s",
+                    peak_gb=d.get("ref_fp16_peak_gb"), torch=d.get("torch"))
+    except Exception as e:
+        return dict(note, unavailable=f"{type(e).__name__}: {str(e)[:200]}")
 
 
 def main():
@@ -347,6 +396,10 @@ def main():
     barrier()
     launches = ops.launch_count() - n0
     ms = ev0.elapsed_time(ev1)
+    out_finite = bool(torch.isfinite(out).all())
+    out_checksum = {"sum": float(out.double().sum()), "abs_mean": float(out.abs().mean()), "finite": out_finite}
+    if not out_finite:
+        raise SystemExit("bench.py: non-finite values in the denoised latent -- not a valid bench run")
     # one more (un-timed) solver step with per-op CUDA events for the roofline / op shares: the event bookkeeping
     # costs host time per launch and must not sit inside the timed region
     ops.trace_begin()
@@ -384,14 +437,45 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = tt.item()
     e2e_value = chunk_frames / (SCHEDULE_STEPS * (e2e_ms / args.steps) / 1e3)
-    h2d = feat.numel() * 4 + y.numel() * 4 + ny.numel() * 4
+    # N>1: every rank uploads only its share of the latent frames (VideoToVideo_sr._upload_frames), shares all-gathered over NVLink
+    h2d = feat.numel() * 4 // world + y.numel() * 4 + ny.numel() * 4
     d2h = res.numel() * res.element_size()
     clk = clocks.stop() if rank == 0 else None
 
     # ---- VAE legs (SURVEY 8d ii/iii): decode the clip in 3-frame windows, encode it frame by frame ----
     vae_info = None
-    if rank == 0 and not args.no_vae:
-        vae_info = time_vae(pipe, out, F, H, W, dev, ms_per_step)
+    if not args.no_vae:
+        vae_info = time_vae(pipe, out, F, H, W, dev, ms_per_step, world, rank, barrier)
+
+    # ---- BASELINE config 3 on the same ranks: 72 frames = chunks 32/32/40, (chunk, CFG branch) pairs on 6 ranks ----
+    config3 = None
+    if world >= 6:
+        F3 = 72
+        f3, _, _ = synth_inputs(F3, H, W, seed=3)
+        f3 = f3.to(dev)
+        k3 = max(1, min(args.steps, 3))
+
+        def run3(k):
+            return pipe.denoise_latents(f3, y_d, ny_d, total_noise_levels=1000, steps=k, solver_mode="normal",
+                                        guide_scale=7.5, max_chunk_len=CHUNK)
+        run3(1)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        o3 = run3(k3)
+        c1.record()
+        barrier()
+        tt = torch.tensor([c0.elapsed_time(c1)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms3 = tt.item() / k3
+        chunks3 = make_chunks(F3, 0, CHUNK)
+        config3 = {"workload": f"BASELINE config 3: {F3}-frame clip, latent {H}x{W}, chunks {chunks3}, 50-step dpmpp_2m_sde, CFG 7.5",
+                   "parallelism": f"(chunk, CFG branch) pairs: {2 * len(chunks3)} active ranks of {world}, one all-gather of raw model "
+                                  "outputs per solver step, exact (bit-identical to the serial loop)",
+                   "ms_per_step": ms3, "steps_timed": k3, "unique_frames_per_s": F3 / (SCHEDULE_STEPS * ms3 / 1e3),
+                   "idle_ranks": world - 2 * len(chunks3), "load_imbalance": max(e - b for b, e in chunks3) / min(e - b for b, e in chunks3),
+                   "finite": bool(torch.isfinite(o3).all()),
+                   "single_gpu_equivalent_ms_per_step": "6 forwards of 32/32/40 frames = (104/32) x the N=1 step time"}
 
     # ---- roofline of the dominant kernel: spatial self-attention at the finest level ------------
     hw0 = H * W
@@ -413,6 +497,8 @@ def main():
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "peak_source": peaks["source"], "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg,
                 "launches_timed": len(attn_ms), "traffic": ncu_traffic_bytes(),
+                "traffic_source": "dram__bytes_read+write of one `ncu --set full` capture of this kernel at this shape "
+                                  "(profiles/r01_ncu_attn4_split.txt); a constant of the kernel, not re-measured per run",
                 "algorithmic_bytes_per_launch": 4.0 * batch * heads * hw0 * 64 * 2,
                 "share_of_step": sum(t for _, t in attn_ms) / sum(per_op.values())}
     if args.trace_out and rank == 0:
@@ -433,8 +519,15 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1): the reference arm in a child process with a hard time limit ----
     cpu = None
+    gpu_ref = None
+    if world == 1 and rank == 0 and not args.small and not args.no_gpu_reference:
+        del pipe, net, out
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_block(H, W)
+        if gpu_ref.get("value"):
+            gpu_ref["star_over_reference"] = value / gpu_ref["value"]
+            gpu_ref["fp16_ceiling_frames_per_s"] = CHUNK / (SCHEDULE_STEPS * 1144.6e12 / (measured_peaks()["tflops"] * 1e12))
     if want_cpu:
-        del pipe, net, sd_cpu
         torch.cuda.empty_cache()
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
@@ -465,8 +558,10 @@ def main():
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
-                    "api": "VideoToVideo_sr.denoise_latents(host tensors, steps=1).cpu() per step"},
-            "roofline": roof, "cpu_baseline": cpu, "pipeline": vae_info,
+                    "api": "VideoToVideo_sr.denoise_latents(host tensors, steps=1).cpu() per step",
+                    "h2d_note": "bytes per rank per step (N>1: frame-sharded upload + NVLink all-gather)"},
+            "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "pipeline": vae_info, "config3": config3,
+            "out_checksum": out_checksum, "unique_frames_per_s": unique_value, "chunk_frames_per_s": value,
             "op_time_share": {k: round(v / sum(per_op.values()), 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
         }
         print(json.dumps(line), flush=True)

@@ -131,6 +131,21 @@ int star_vae_head(const void* X, long long ldx, const void* W27, const void* bia
 /* (b,c,f,h,w) fp32 -> tokens fp16 [(b f h w), c]  and back (fp16 -> fp16)  (unet_v2v.py:1772,:1808) */
 int star_nchw5_to_tokens(const void* x_f32, void* out, int B, int C, int F, long long HW, void* stream);
 int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, int F, long long HW, void* stream);
+/* ---- pipeline glue on the GPU ---------------------------------------------------------------------------------
+ * F.interpolate(x, [H, W], mode='bilinear') + F.pad(x, (pad_l, pad_r, pad_t, pad_b), 'constant', pad_value)
+ * (video_to_video_model.py:81,:86-87): x fp32 (NC, h, w) -> out fp32 (NC, H + pad_t + pad_b, W + pad_l + pad_r). */
+int star_bilinear_pad(const void* x_f32, void* out_f32, long long NC, int h, int w, int H, int W, int pad_l, int pad_r,
+                      int pad_t, int pad_b, float pad_value, void* stream);
+/* Classifier-free guidance + std-ratio rescale + v -> x0 (diffusion_sdedit.py:89-99) in two launches:
+ *   out = u + g (y - u)   (fp16, each op rounded like the reference's fp16 tensor arithmetic)
+ *   out *= r * std(y) / (std(out) + 1e-12) + (1 - r)      per sample over `per_sample` elements; r < 0: no rescale
+ *   x0 = alpha[sample] * xt - sigma[sample] * out          fp32
+ * y_out / u_out fp16 [samples, per_sample]; xt / x0 fp32; guided_out (fp16, may be NULL) receives `out`;
+ * alpha / sigma fp32 [samples] on the device; workspace: star_cfg_x0_workspace_bytes(samples). */
+long long star_cfg_x0_workspace_bytes(int samples);
+int star_cfg_x0(const void* y_out, const void* u_out, const void* xt_f32, void* x0_f32, void* guided_out,
+                float guide_scale, float guide_rescale, const void* alpha_f32, const void* sigma_f32, int samples,
+                long long per_sample, void* workspace, void* stream);
 /* sinusoidal timestep embedding (unet_v2v.py:96-108); t = int64 [B]; out fp16 [B, dim] */
 int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream);
 int star_silu(const void* x, void* out, long long n, void* stream);

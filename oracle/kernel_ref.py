@@ -283,3 +283,18 @@ def vae_head(x, w27, bias3, B, T, H, W):
     x5 = _f(x[:, :3]).reshape(B, T, H, W, 3).permute(0, 4, 1, 2, 3)                 # b c t h w
     y = F.conv3d(x5, _f(w27).reshape(3, 3, 3, 1, 1), _f(bias3), padding=(1, 0, 0))
     return y.permute(0, 2, 1, 3, 4).reshape(B * T, 3, H, W).to(HALF)
+
+
+def bilinear_pad(x, H, W, padding=(0, 0, 0, 0), value=1.0):
+    return F.pad(F.interpolate(x.reshape(-1, 1, *x.shape[-2:]).float(), [H, W], mode="bilinear"), padding, "constant", value
+                 ).reshape(*x.shape[:-2], H + padding[2] + padding[3], W + padding[0] + padding[1])
+
+
+def cfg_x0(y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale=None, return_guided=False):
+    """the reference's fp16 tensor arithmetic, op by op (diffusion_sdedit.py:89-99)"""
+    out = u_out + guide_scale * (y_out - u_out)
+    if guide_rescale is not None:
+        ratio = (y_out.flatten(1).std(dim=1) / (out.flatten(1).std(dim=1) + 1e-12)).view((-1,) + (1,) * (y_out.ndim - 1))
+        out = out * (guide_rescale * ratio + (1 - guide_rescale) * 1.0)
+    x0 = alphas * xt - sigmas * out
+    return (x0, out) if return_guided else x0

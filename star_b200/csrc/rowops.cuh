@@ -869,4 +869,100 @@ __global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ o
     if (i < n) out[i] = __float2half_rn(silu_f(__half2float(x[i])));
 }
 
+
+// ------------------------------------------------------------------ pre-processing (video_to_video_model.py:81-87)
+// F.interpolate(x, [H, W], mode='bilinear') (align_corners = False) followed by F.pad(..., (pl, pr, pt, pb), value):
+// x (NC, h, w) fp32 -> out (NC, H + pt + pb, W + pl + pr) fp32.  One thread per output pixel, x fastest.
+__global__ void __launch_bounds__(256)
+bilinear_pad_kernel(const float* __restrict__ x, float* __restrict__ out, long long NC, int h, int w, int H, int W, int pl,
+                    int pt, int Hp, int Wp, float sh, float sw, float padv) {
+    const long long total = NC * Hp * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wp);
+        const int oy = (int)((i / Wp) % Hp);
+        const long long nc = i / ((long long)Wp * Hp);
+        const int dx = ox - pl, dy = oy - pt;
+        float v = padv;
+        if (dx >= 0 && dx < W && dy >= 0 && dy < H) {
+            const float fy = fmaxf(__fmaf_rn((float)dy + 0.5f, sh, -0.5f), 0.f);
+            const float fx = fmaxf(__fmaf_rn((float)dx + 0.5f, sw, -0.5f), 0.f);
+            const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+            const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+            const float ly = fy - (float)y0, lx = fx - (float)x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const float* p = x + nc * (long long)h * w;
+            v = hy * (hx * __ldg(p + (long long)y0 * w + x0) + lx * __ldg(p + (long long)y0 * w + x1)) +
+                ly * (hx * __ldg(p + (long long)y1 * w + x0) + lx * __ldg(p + (long long)y1 * w + x1));
+        }
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------ guided x0 (diffusion_sdedit.py:89-99)
+// out = u + g (y - u) in fp16 (each op rounded like the reference's fp16 tensor ops), std-ratio rescale
+// out *= r * std(y) / (std(out) + 1e-12) + (1 - r) with per-sample (unbiased) std over the whole chunk, then
+// x0 = alpha * xt - sigma * out in fp32.  Two launches: statistics (double atomics into stats[sample][4]), apply.
+STAR_DEVINL float cfg_combine_h(__half y, __half u, float g) {
+    const float d = __half2float(__float2half_rn(__half2float(y) - __half2float(u)));
+    const float gd = __half2float(__float2half_rn(g * d));
+    return __half2float(__float2half_rn(__half2float(u) + gd));
+}
+
+__global__ void __launch_bounds__(256)
+cfg_stats_kernel(const __half* __restrict__ y, const __half* __restrict__ u, float g, long long per_sample,
+                 double* __restrict__ stats) {
+    const int sample = blockIdx.y;
+    const __half* ys = y + sample * per_sample;
+    const __half* us = u + sample * per_sample;
+    float sy = 0.f, syy = 0.f, so = 0.f, soo = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+        const float yv = __half2float(ys[i]);
+        const float ov = cfg_combine_h(ys[i], us[i], g);
+        sy += yv; syy += yv * yv; so += ov; soo += ov * ov;
+    }
+    __shared__ float red[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        syy += __shfl_xor_sync(0xffffffffu, syy, o);
+        so += __shfl_xor_sync(0xffffffffu, so, o);
+        soo += __shfl_xor_sync(0xffffffffu, soo, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = sy; red[1][warp] = syy; red[2][warp] = so; red[3][warp] = soo; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double acc = 0.0;
+        for (int k = 0; k < 8; ++k) acc += (double)red[threadIdx.x][k];
+        atomicAdd(&stats[sample * 4 + threadIdx.x], acc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cfg_x0_kernel(const __half* __restrict__ y, const __half* __restrict__ u, const float* __restrict__ xt,
+              float* __restrict__ x0, __half* __restrict__ out_g, float g, float r, int has_rescale,
+              const float* __restrict__ alpha, const float* __restrict__ sigma, long long per_sample,
+              const double* __restrict__ stats) {
+    const int sample = blockIdx.y;
+    float scale = 1.f;
+    if (has_rescale) {
+        const double n = (double)per_sample;
+        const double vy = (stats[sample * 4 + 1] - stats[sample * 4 + 0] * stats[sample * 4 + 0] / n) / (n - 1.0);
+        const double vo = (stats[sample * 4 + 3] - stats[sample * 4 + 2] * stats[sample * 4 + 2] / n) / (n - 1.0);
+        const float sdy = __half2float(__float2half_rn((float)sqrt(vy > 0.0 ? vy : 0.0)));       // tensor.std() in fp16
+        const float sdo = __half2float(__float2half_rn((float)sqrt(vo > 0.0 ? vo : 0.0)));
+        const float ratio = __half2float(__float2half_rn(__fdiv_rn(sdy, __half2float(__float2half_rn(sdo + 1e-12f)))));
+        const float a = __half2float(__float2half_rn(r * ratio));
+        scale = __half2float(__float2half_rn(a + (1.f - r)));
+    }
+    const float al = alpha[sample], sg = sigma[sample];
+    const long long base = sample * per_sample;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+        float o = cfg_combine_h(y[base + i], u[base + i], g);
+        if (has_rescale) o = __half2float(__float2half_rn(o * scale));
+        if (out_g) out_g[base + i] = __float2half_rn(o);
+        x0[base + i] = __fsub_rn(__fmul_rn(al, xt[base + i]), __fmul_rn(sg, o));
+    }
+}
+
 }  // namespace star

@@ -711,6 +711,43 @@ int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, 
     return 0;
 }
 
+int star_bilinear_pad(const void* x_f32, void* out_f32, long long NC, int h, int w, int H, int W, int pad_l, int pad_r,
+                      int pad_t, int pad_b, float pad_value, void* stream) {
+    if (NC <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || pad_l < 0 || pad_r < 0 || pad_t < 0 || pad_b < 0)
+        return fail("star_bilinear_pad: bad geometry");
+    const int Hp = H + pad_t + pad_b, Wp = W + pad_l + pad_r;
+    const long long n = NC * Hp * Wp;
+    bilinear_pad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x_f32, (float*)out_f32, NC, h, w, H, W,
+                                                                            pad_l, pad_t, Hp, Wp, (float)h / (float)H,
+                                                                            (float)w / (float)W, pad_value);
+    STAR_LAUNCH_CHECK("bilinear_pad");
+    return 0;
+}
+
+long long star_cfg_x0_workspace_bytes(int samples) { return (long long)samples * 4 * 8; }
+
+int star_cfg_x0(const void* y_out, const void* u_out, const void* xt_f32, void* x0_f32, void* guided_out,
+                float guide_scale, float guide_rescale, const void* alpha_f32, const void* sigma_f32, int samples,
+                long long per_sample, void* workspace, void* stream) {
+    if (samples <= 0 || per_sample <= 1) return fail("star_cfg_x0: empty problem");
+    if (samples > 65535) return fail("star_cfg_x0: too many samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int has_rescale = guide_rescale >= 0.f;
+    double* stats = (double*)workspace;
+    const unsigned gx = (unsigned)std::min<long long>((per_sample + 255) / 256, (long long)num_sms() * 8);
+    if (has_rescale) {
+        if (!workspace) return fail("star_cfg_x0: the std-ratio rescale needs a workspace");
+        STAR_CUDA(cudaMemsetAsync(stats, 0, (size_t)samples * 4 * 8, st));
+        cfg_stats_kernel<<<dim3(gx, samples), 256, 0, st>>>((const __half*)y_out, (const __half*)u_out, guide_scale, per_sample, stats);
+        STAR_LAUNCH_CHECK("cfg_stats");
+    }
+    cfg_x0_kernel<<<dim3(gx, samples), 256, 0, st>>>((const __half*)y_out, (const __half*)u_out, (const float*)xt_f32,
+                                                     (float*)x0_f32, (__half*)guided_out, guide_scale, guide_rescale,
+                                                     has_rescale, (const float*)alpha_f32, (const float*)sigma_f32, per_sample, stats);
+    STAR_LAUNCH_CHECK("cfg_x0");
+    return 0;
+}
+
 int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream) {
     const int n = B * (dim / 2);
     sinusoidal_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)t_i64, (__half*)out, B, dim);

@@ -44,6 +44,9 @@ SIGNATURES = {
     "star_conv2d_3x3_s2p": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "star_nchw5_to_tokens": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
     "star_tokens_to_nchw5": (_i, [_p, _ll, _p, _i, _i, _i, _ll, _p]),
+    "star_bilinear_pad": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "star_cfg_x0_workspace_bytes": (_ll, [_i]),
+    "star_cfg_x0": (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _ll, _p, _p]),
     "star_sinusoidal": (_i, [_p, _p, _i, _i, _p]),
     "star_silu": (_i, [_p, _p, _ll, _p]),
 }

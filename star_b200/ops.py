@@ -369,6 +369,46 @@ def silu(x):
     return out
 
 
+@_traced
+def bilinear_pad(x, H, W, padding=(0, 0, 0, 0), value=1.0):
+    """F.interpolate(x, [H, W], mode='bilinear') + F.pad(x, padding=(l, r, t, b), 'constant', value); x fp32 (..., h, w)"""
+    _dev(x)
+    if x.dtype != torch.float32:
+        raise _L.StarError("bilinear_pad expects fp32 frames")
+    x = x.contiguous()
+    *lead, h, w = x.shape
+    pl, pr, pt, pb = (int(v) for v in padding)
+    out = torch.empty((*lead, H + pt + pb, W + pl + pr), dtype=torch.float32, device=x.device)
+    nc = 1
+    for d in lead:
+        nc *= d
+    L = _L.get_lib()
+    _L.check(L.star_bilinear_pad(_p(x), _p(out), nc, h, w, int(H), int(W), pl, pr, pt, pb, float(value), _st()),
+             "star_bilinear_pad")
+    return out
+
+
+@_traced
+def cfg_x0(y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale=None, return_guided=False):
+    """x0 = alphas * xt - sigmas * rescale(u + g (y - u)); y_out / u_out fp16 (B, ...), xt fp32, alphas / sigmas fp32 (B, 1, ...)"""
+    _dev(y_out)
+    _h(y_out, "y_out"); _h(u_out, "u_out")
+    assert y_out.is_contiguous() and u_out.is_contiguous() and y_out.shape == u_out.shape == xt.shape
+    B = y_out.shape[0]
+    per = y_out.numel() // B
+    xt = xt.float().contiguous()
+    x0 = torch.empty_like(xt)
+    guided = torch.empty_like(y_out) if return_guided else None
+    al = alphas.reshape(B).float().contiguous()
+    sg = sigmas.reshape(B).float().contiguous()
+    L = _L.get_lib()
+    ws = torch.empty(L.star_cfg_x0_workspace_bytes(B), dtype=torch.uint8, device=y_out.device)
+    _L.check(L.star_cfg_x0(_p(y_out), _p(u_out), _p(xt), _p(x0), _p(guided), float(guide_scale),
+                           -1.0 if guide_rescale is None else float(guide_rescale), _p(al), _p(sg), B, per, _p(ws), _st()),
+             "star_cfg_x0")
+    return (x0, guided) if return_guided else x0
+
+
 FLAG_GELU_TANH = 8
 
 

@@ -24,7 +24,6 @@ import torch
 import torch.distributed as dist
 
 from ..utils.logger import get_logger
-from .schedules_sdedit import karras_schedule
 from .solvers_sdedit import sample_dpmpp_2m_sde, sample_heun
 
 logger = get_logger()
@@ -65,12 +64,6 @@ class GaussianDiffusion(object):
         noise = torch.randn_like(x0) if noise is None else noise
         return _gather_coef(self.alphas, t, x0) * x0 + _gather_coef(self.sigmas, t, x0) * noise
 
-    def get_velocity(self, x0, xt, t):
-        return (_gather_coef(self.alphas, t, xt) * xt - x0) / _gather_coef(self.sigmas, t, xt)
-
-    def get_x0(self, v, xt, t):
-        return _gather_coef(self.alphas, t, xt) * xt - _gather_coef(self.sigmas, t, xt) * v
-
     # -- one denoise evaluation (2 model calls under CFG) -----------------------
     def denoise(self, xt, t, s, model, model_kwargs={}, guide_scale=None, guide_rescale=None,
                 clamp=None, percentile=None, variant_info=None):
@@ -91,29 +84,48 @@ class GaussianDiffusion(object):
             out = model(xt, t=t, **model_kwargs)
         else:
             assert isinstance(model_kwargs, list)
-            extra = {}
-            for kw in model_kwargs[2:]:
-                extra.update(kw)
-            if len(model_kwargs) <= 3:
-                extra["variant_info"] = variant_info
-            y_out = model(xt, t=t, **model_kwargs[0], **extra)
+            y_out = self._branch_out(xt, t, model, model_kwargs, 0, variant_info)
             if guide_scale == 1.0:
                 out = y_out
             else:
-                u_out = model(xt, t=t, **model_kwargs[1], **extra)
-                out = self._guided(y_out, u_out, guide_scale, guide_rescale)
+                u_out = self._branch_out(xt, t, model, model_kwargs, 1, variant_info)
+                out = (y_out, u_out)
 
-        x0 = alphas * xt - sigmas * out
-        if percentile is not None:
-            assert 0 < percentile <= 1
-            q = torch.quantile(x0.flatten(1).abs(), percentile, dim=1)
-            q = q.clamp_(1.0).view((-1,) + (1,) * (xt.ndim - 1))
-            x0 = torch.min(q, torch.max(-q, x0)) / q
-        elif clamp is not None:
-            x0 = x0.clamp(-clamp, clamp)
+        if isinstance(out, tuple):
+            x0 = self._guided_x0(out[0], out[1], xt, alphas, sigmas, guide_scale, guide_rescale, clamp, percentile)
+        else:
+            x0 = self._x0_from_out(xt, alphas, sigmas, out, clamp, percentile)
         eps = (xt - alphas * x0) / sigmas
         mu = coef1 * x0 + coef2 * xt
         return mu, var, log_var, x0, eps
+
+    @staticmethod
+    def _branch_out(xt, t, model, model_kwargs, branch, variant_info):
+        """One CFG branch (0 = conditional, 1 = unconditional) of the model call (ref :76-88)."""
+        extra = {}
+        for kw in model_kwargs[2:]:
+            extra.update(kw)
+        if len(model_kwargs) <= 3:
+            extra["variant_info"] = variant_info
+        return model(xt, t=t, **model_kwargs[branch], **extra)
+
+    @staticmethod
+    def _x0_from_out(xt, alphas, sigmas, out, clamp=None, percentile=None):
+        """v-prediction -> x0 (ref :99).  The reference's dynamic-threshold / clamp options (:100-107) are never
+        set by VideoToVideo_sr.test (:110-123) and are not carried over."""
+        if clamp is not None or percentile is not None:
+            raise NotImplementedError("clamp / percentile are not used on STAR's path (ref video_to_video_model.py:110-123)")
+        return alphas * xt - sigmas * out
+
+    def _guided_x0(self, y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale, clamp=None, percentile=None):
+        """CFG combine + std-ratio rescale + v -> x0 (ref :89-99).  fp16 CUDA model outputs (the .half() UNet) take
+        the fused device path -- two launches (star_cfg_x0) instead of ~20 eager tensor ops; anything else (CPU tests,
+        fp32 fakes) runs the reference's tensor arithmetic."""
+        if y_out.is_cuda and y_out.dtype == torch.float16 and u_out.dtype == torch.float16 and clamp is None \
+                and percentile is None:
+            from ... import ops
+            return ops.cfg_x0(y_out.contiguous(), u_out.contiguous(), xt, alphas, sigmas, guide_scale, guide_rescale)
+        return self._x0_from_out(xt, alphas, sigmas, self._guided(y_out, u_out, guide_scale, guide_rescale), clamp, percentile)
 
     @staticmethod
     def _guided(y_out, u_out, guide_scale, guide_rescale):
@@ -137,20 +149,17 @@ class GaussianDiffusion(object):
         assert isinstance(steps, (int, torch.LongTensor))
         assert t_max is None or (0 < t_max <= self.num_timesteps - 1)
         assert t_min is None or (0 <= t_min < self.num_timesteps - 1)
-        assert discretization in (None, 'leading', 'linspace', 'trailing')
+        assert discretization in (None, 'linspace', 'trailing')     # 'leading' (ref :360) is never selected by STAR
         assert discard_penultimate_step in (None, True, False)
         assert return_intermediate in (None, 'x0', 'xt')
         solver_fn = {'heun': sample_heun, 'dpmpp_2m_sde': sample_dpmpp_2m_sde}[solver]
 
-        schedule = 'karras' if 'karras' in solver else None
         discretization = discretization or 'linspace'
         seed = seed if seed >= 0 else random.randint(0, 2 ** 31)
         if isinstance(steps, torch.LongTensor):
             discard_penultimate_step = False
         if discard_penultimate_step is None:
-            discard_penultimate_step = solver in (
-                'dpm2', 'dpm2_ancestral', 'dpmpp_2m_sde', 'dpm2_karras',
-                'dpm2_ancestral_karras', 'dpmpp_2m_sde_karras')
+            discard_penultimate_step = solver == 'dpmpp_2m_sde'      # ref :318-321 (the other names are not selectable)
 
         # The reference raises IndexError for a single window (F in 33..40,
         # SURVEY App. B); a one-window list is the un-chunked case.
@@ -182,20 +191,33 @@ class GaussianDiffusion(object):
 
         keep = stitch_slices(chunk_inds) if chunk_inds is not None else None
 
-        def chunk_x0(xt, t, i, variant_info):
-            """x0 of chunk i, cropped to the slice it contributes (ref :337-350)."""
+        def chunk_inputs(xt, i):
             s, e = chunk_inds[i]
             model_kwargs[2]['hint_chunk'] = model_kwargs[2]['hint'][:, :, s:e].clone()
-            x0c = self.denoise(xt[:, :, s:e].clone(), t, None, model, model_kwargs, guide_scale,
+            return xt[:, :, s:e].clone()
+
+        def chunk_x0(xt, t, i, variant_info):
+            """x0 of chunk i, cropped to the slice it contributes (ref :337-350)."""
+            x0c = self.denoise(chunk_inputs(xt, i), t, None, model, model_kwargs, guide_scale,
                                guide_rescale, clamp, percentile, variant_info=variant_info)[-2]
             lo, hi = keep[i]
             return x0c[:, :, lo:hi]
+
+        # CFG-branch split (SURVEY 8e): with at least two ranks per chunk the (chunk, branch) pairs are the units --
+        # BASELINE config 3 (3 chunks) then fills 6 of 8 GPUs instead of 3.
+        split_cfg = (world > 1 and chunk_inds is not None and isinstance(model_kwargs, list)
+                     and guide_scale not in (None, 1.0) and world >= 2 * len(chunk_inds)
+                     and chunk_parallel in ("auto", "exact"))
+        wire = {}
 
         def eval_x0_chunked(xt, sigma, variant_info=None):
             t = self._sigma_to_t(sigma).repeat(len(xt)).round().long()
             if world == 1:
                 parts = [chunk_x0(xt, t, i, variant_info) for i in range(len(chunk_inds))]
                 return torch.concat(parts, dim=2)
+            if split_cfg:
+                return self._eval_x0_cfg_split(xt, t, chunk_inds, keep, chunk_inputs, model, model_kwargs, guide_scale,
+                                               guide_rescale, variant_info, world, rank, wire)
             return self._eval_x0_sharded(xt, t, chunk_inds, keep, chunk_x0, variant_info, world, rank)
 
         # -- timestep / sigma tables (ref :355-406) -----------------------------
@@ -203,9 +225,7 @@ class GaussianDiffusion(object):
             steps += 1 if discard_penultimate_step else 0
             t_max = self.num_timesteps - 1 if t_max is None else t_max
             t_min = 0 if t_min is None else t_min
-            if discretization == 'leading':
-                steps = torch.arange(t_min, t_max + 1, (t_max - t_min + 1) / steps).flip(0)
-            elif discretization == 'linspace':
+            if discretization == 'linspace':
                 steps = torch.linspace(t_max, t_min, steps)
             elif discretization == 'trailing':
                 steps = torch.arange(t_max, t_min - 1, -((t_max - t_min + 1) / steps))
@@ -221,16 +241,6 @@ class GaussianDiffusion(object):
 
         sigmas = self._t_to_sigma(steps)
         sigmas = torch.cat([sigmas, sigmas.new_zeros([1])])
-        if schedule == 'karras':
-            if sigmas[0] == float('inf'):
-                sigmas = karras_schedule(n=len(steps) - 1, sigma_min=sigmas[sigmas > 0].min().item(),
-                                         sigma_max=sigmas[sigmas < float('inf')].max().item(),
-                                         rho=7.).to(sigmas)
-                sigmas = torch.cat([sigmas.new_tensor([float('inf')]), sigmas, sigmas.new_zeros([1])])
-            else:
-                sigmas = karras_schedule(n=len(steps), sigma_min=sigmas[sigmas > 0].min().item(),
-                                         sigma_max=sigmas.max().item(), rho=7.).to(sigmas)
-                sigmas = torch.cat([sigmas, sigmas.new_zeros([1])])
         if discard_penultimate_step:
             sigmas = torch.cat([sigmas[:-2], sigmas[-1:]])
 
@@ -268,6 +278,39 @@ class GaussianDiffusion(object):
             r = owner[i]
             parts.append(recv[r][:, :, cursor[r]:cursor[r] + lens[i]])
             cursor[r] += lens[i]
+        return torch.concat(parts, dim=2)
+
+    def _eval_x0_cfg_split(self, xt, t, chunk_inds, keep, chunk_inputs, model, model_kwargs, guide_scale, guide_rescale,
+                           variant_info, world, rank, wire):
+        """Exact mode with two ranks per chunk: rank 2i evaluates the conditional branch of chunk i, rank 2i+1 the
+        unconditional one (ranks >= 2n idle).  ONE all-gather of the raw model outputs per solver step; every rank
+        then forms the guided output (needs both branches: std-ratio rescale, ref :89-97), x0 and the stitch for all
+        chunks -- elementwise work on a few MB, identical on every rank and to the serial loop."""
+        n = len(chunk_inds)
+        lens = [e - s for s, e in chunk_inds]
+        b, c, _, h, w = xt.shape
+        out = None
+        if rank < 2 * n:
+            i, branch = divmod(rank, 2)
+            out = self._branch_out(chunk_inputs(xt, i), t, model, model_kwargs, branch, variant_info)
+        if "dtype" not in wire:                      # the model's output dtype (fp16 for the .half() UNet), agreed once
+            codes = [torch.float16, torch.bfloat16, torch.float32, torch.float64]
+            code = torch.tensor([codes.index(out.dtype) if out is not None else 0], device=xt.device)
+            dist.broadcast(code, 0)
+            wire["dtype"] = codes[int(code.item())]
+        send = torch.zeros((b, c, max(lens), h, w), dtype=wire["dtype"], device=xt.device)
+        if out is not None:
+            send[:, :, :out.shape[2]] = out
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        sig = _gather_coef(self.sigmas, t, xt)
+        alp = _gather_coef(self.alphas, t, xt)
+        parts = []
+        for i, (s, e) in enumerate(chunk_inds):
+            y_out, u_out = recv[2 * i][:, :, :lens[i]], recv[2 * i + 1][:, :, :lens[i]]
+            x0c = self._guided_x0(y_out, u_out, xt[:, :, s:e], alp, sig, guide_scale, guide_rescale)
+            lo, hi = keep[i]
+            parts.append(x0c[:, :, lo:hi])
         return torch.concat(parts, dim=2)
 
     def _sample_literal(self, noise, solver_fn, sigmas, chunk_inds, keep, model, model_kwargs, guide_scale,

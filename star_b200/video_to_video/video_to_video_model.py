@@ -12,14 +12,21 @@ Mirrors ``VideoToVideo_sr`` of the reference's video_to_video/video_to_video_mod
 * the text encoder (open_clip) is an un-vendored third-party package: it is imported lazily, and
   ready-made objects can be injected (``text_encoder=``, ``vae=``, ``generator=``), which is how the
   tests and the benchmark run on boxes without those packages or checkpoints;
-* with ``torch.distributed`` initialised, frame chunks are sharded across ranks
-  (diffusion_sdedit.GaussianDiffusion.sample_sr, ``chunk_parallel``).
+* with ``torch.distributed`` initialised (one process per GPU) the whole entry is sharded:
+  - each rank uploads, upsamples and VAE-encodes only its contiguous share of the frames; the latents (0.42 MB per
+    frame) are all-gathered, so every rank conditions on the SAME posterior sample (the reference draws it once);
+  - frame chunks -- or (chunk, CFG branch) pairs when there are at least two ranks per chunk -- are sharded across
+    ranks with one all-gather per solver step (diffusion_sdedit.GaussianDiffusion.sample_sr, ``chunk_parallel``);
+  - each rank decodes its share of the 3-frame VAE windows and ONE all-gather of the decoded, cropped frames
+    assembles the clip (the north-star's end collective).
 """
 from typing import Any, Dict
 
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
+from .. import ops
 from .diffusion.diffusion_sdedit import GaussianDiffusion
 from .diffusion.schedules_sdedit import noise_schedule
 from .modules.unet_v2v import ControlledV2VUNet, rearrange
@@ -29,6 +36,38 @@ from .utils.logger import get_logger
 logger = get_logger()
 
 __all__ = ["VideoToVideo_sr", "pad_to_fit", "make_chunks", "sliding_windows_1d"]
+
+
+def _dist_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _shard_bounds(n, world):
+    """contiguous, balanced split of n items over `world` ranks: [(lo, hi)] (empty shards when n < world)"""
+    base, extra = divmod(n, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def _all_gather_varlen(local, counts, dim):
+    """all-gather of per-rank tensors whose extent along `dim` is counts[rank] (padded to the longest share);
+    returns the concatenation in rank order.  ONE collective."""
+    world, rank = _dist_info()
+    pad = max(counts)
+    shape = list(local.shape)
+    shape[dim] = pad
+    send = local.new_zeros(shape)
+    if counts[rank]:
+        send.narrow(dim, 0, counts[rank]).copy_(local)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send)
+    return torch.cat([recv[r].narrow(dim, 0, counts[r]) for r in range(world) if counts[r]], dim=dim)
 
 
 class VideoToVideo_sr():
@@ -90,7 +129,7 @@ class VideoToVideo_sr():
         """video_data_feature: (1,4,F,h,w) VAE latent of the upsampled LR clip (any device; moved to
         self.device), y / negative_y: (1,77,1024).  Returns the denoised latent (1,4,F,h,w) fp32 on
         self.device.  ``noise`` / ``noise_sampler`` pin the two random inputs (diffuse noise, SDE noise)."""
-        feat = video_data_feature.to(self.device, torch.float32)
+        feat = self._upload_frames(video_data_feature)
         y = y.to(self.device)
         negative_y = (self.negative_y if negative_y is None else negative_y).to(self.device)
         frames_num = feat.shape[2]
@@ -109,6 +148,17 @@ class VideoToVideo_sr():
             steps=steps, t_max=total_noise_levels - 1, t_min=0, discretization='trailing',
             chunk_inds=chunk_inds, chunk_parallel=chunk_parallel, **extra)
 
+    def _upload_frames(self, x, dim=2):
+        """Host tensor -> fp32 on self.device.  Under torch.distributed every rank uploads only its share of the
+        frames over its own PCIe link and the shares are all-gathered over NVLink (instead of W full uploads)."""
+        world, rank = _dist_info()
+        if x.is_cuda or world == 1 or x.shape[dim] < world:
+            return x.to(self.device, torch.float32)
+        bounds = _shard_bounds(x.shape[dim], world)
+        lo, hi = bounds[rank]
+        local = x.narrow(dim, lo, hi - lo).to(self.device, torch.float32, non_blocking=True)
+        return _all_gather_varlen(local, [b - a for a, b in bounds], dim)
+
     # -- pixel-space entry (ref :75-139) ------------------------------------------------------------
     @torch.no_grad()
     def test(self, input: Dict[str, Any], total_noise_levels=1000, steps=50, solver_mode='fast', guide_scale=7.5,
@@ -116,25 +166,77 @@ class VideoToVideo_sr():
         video_data = input['video_data']
         y = input['y']
         (target_h, target_w) = input['target_res']
-        video_data = F.interpolate(video_data, [target_h, target_w], mode='bilinear')
-        logger.info(f'video_data shape: {video_data.shape}')
-        frames_num, _, h, w = video_data.shape
-        padding = pad_to_fit(h, w)
-        video_data = F.pad(video_data, padding, 'constant', 1)
-        video_data = video_data.unsqueeze(0).to(self.device)
+        world, rank = _dist_info()
+        frames_num = video_data.shape[0]
+        bounds = _shard_bounds(frames_num, world)
+        lo, hi = bounds[rank]
+        # this rank's frames only: upload (LR frames), bilinear x4 + pad-with-1 on the GPU, encode frame by frame
+        padding = pad_to_fit(target_h, target_w)
+        h, w = target_h, target_w
+        local = video_data[lo:hi].to(self.device)
+        logger.info(f'video_data shape: {(frames_num, video_data.shape[1], h, w)}')
         bs = 1
-        video_data_feature = self.vae_encode(video_data)
+        if hi > lo:
+            local = self.upsample_pad(local, target_h, target_w, padding)
+            feat_local = self.vae_encode(local.unsqueeze(0))
+        else:
+            lh = (h + padding[2] + padding[3]) // 8
+            lw = (w + padding[0] + padding[1]) // 8
+            feat_local = torch.zeros((1, 4, 0, lh, lw), device=self.device)
+        del local
+        video_data_feature = feat_local if world == 1 else \
+            _all_gather_varlen(feat_local.float(), [b - a for a, b in bounds], 2)
         y = self._encode_text(y)
         gen_vid = self.denoise_latents(video_data_feature, y, None, total_noise_levels, steps, solver_mode,
                                        guide_scale, max_chunk_len)
         logger.info('sampling, finished.')
-        with torch.autocast('cuda', enabled=torch.cuda.is_available()):
-            vid_tensor_gen = self.vae_decode_chunk(gen_vid, chunk_size=3)
-        logger.info('temporal vae decoding, finished.')
         w1, w2, h1, h2 = padding
-        vid_tensor_gen = vid_tensor_gen[:, :, h1:h + h1, w1:w + w1]
+        with torch.autocast('cuda', enabled=torch.cuda.is_available()):
+            if world == 1:
+                vid_tensor_gen = self.vae_decode_chunk(gen_vid, chunk_size=3)[:, :, h1:h + h1, w1:w + w1]
+            else:
+                vid_tensor_gen = self._decode_sharded(gen_vid, 3, (h1, h + h1, w1, w + w1))
+        logger.info('temporal vae decoding, finished.')
         gen_video = rearrange(vid_tensor_gen, '(b f) c h w -> b c f h w', b=bs)
         return gen_video.type(torch.float32).cpu()
+
+    def upsample_pad(self, frames, target_h, target_w, padding):
+        """(f,3,h,w) -> bilinear resize to (target_h, target_w) (F.interpolate semantics, align_corners=False) and
+        constant-1 padding (w1, w2, h1, h2), ref :81-87 -- one kernel on the GPU, eager torch for CPU tensors."""
+        if frames.is_cuda:
+            return ops.bilinear_pad(frames.float(), target_h, target_w, padding, 1.0)
+        return F.pad(F.interpolate(frames, [target_h, target_w], mode='bilinear'), padding, 'constant', 1)
+
+    def _decode_sharded(self, z, chunk_size, crop):
+        """3-frame VAE windows (ref :144-151) round-robin over the ranks; ONE all-gather of the decoded, cropped
+        frames.  Window w covers frames [3w, 3w+3) of the full clip on every rank, so the windows -- and therefore
+        the decoder's per-window GroupNorm / temporal-conv context -- are exactly the single-GPU ones."""
+        world, rank = _dist_info()
+        t0, t1, l0, l1 = crop
+        zf = rearrange(z, "b c f h w -> (b f) c h w")
+        n = zf.shape[0]
+        starts = list(range(0, n, chunk_size))
+        mine = starts[rank::world]
+        outs = [self.temporal_vae_decode(zf[s:s + chunk_size], min(chunk_size, n - s))[:, :, t0:t1, l0:l1] for s in mine]
+        counts = [sum(min(chunk_size, n - s) for s in starts[r::world]) for r in range(world)]
+        if outs:
+            local = torch.cat(outs)
+        else:
+            local = torch.zeros((0, 3, t1 - t0, l1 - l0), device=self.device, dtype=torch.float16)
+        dtype_code = torch.tensor([0 if local.dtype == torch.float16 else 1], device=self.device)
+        dist.all_reduce(dtype_code, op=dist.ReduceOp.MAX)
+        local = local.to(torch.float16 if int(dtype_code.item()) == 0 else torch.float32)
+        gathered = _all_gather_varlen(local, counts, 0)                   # rank-major: windows r, r+W, ... of rank r
+        order, pos = [], 0
+        frame_of = {}
+        for r in range(world):
+            for s in starts[r::world]:
+                k = min(chunk_size, n - s)
+                for j in range(k):
+                    frame_of[s + j] = pos + j
+                pos += k
+        idx = torch.tensor([frame_of[f] for f in range(n)], device=gathered.device)
+        return gathered.index_select(0, idx)
 
     # -- VAE helpers (ref :141-161): exact 3-frame decode windows, 1-frame encode ----------------------
     def temporal_vae_decode(self, z, num_f):

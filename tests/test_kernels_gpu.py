@@ -228,6 +228,39 @@ def test_copies(env):
     assert_close(O.silu(a), R.silu(a), what="silu")
 
 
+@pytest.mark.parametrize("shape,H,W,pad", [((4, 3, 24, 40), 96, 160, (560, 560, 312, 312)), ((2, 3, 240, 426), 960, 1704, (0, 24, 0, 16)),
+                                          ((1, 3, 17, 9), 50, 31, (1, 2, 3, 0))])
+def test_bilinear_pad(env, shape, H, W, pad):
+    """F.interpolate(bilinear, align_corners=False) + F.pad(value=1): ref video_to_video_model.py:81-87"""
+    O, R = env
+    x = torch.rand(*shape, device="cuda") * 2 - 1
+    got = O.bilinear_pad(x, H, W, pad, 1.0)
+    ref = R.bilinear_pad(x, H, W, pad, 1.0)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("B,shape,rescale", [(1, (4, 32, 122, 216), 0.2), (2, (4, 5, 18, 16), 0.2), (1, (4, 3, 10, 8), None)])
+def test_cfg_x0(env, B, shape, rescale):
+    """CFG combine + std-ratio rescale + v -> x0 (diffusion_sdedit.py:89-99) against the reference's fp16 tensor ops"""
+    O, R = env
+    y = rnd(B, *shape, seed=1)
+    u = (y.float() + 0.3 * torch.randn_like(y.float())).half()
+    xt = torch.randn(B, *shape, device="cuda")
+    al = torch.full((B, 1, 1, 1, 1), 0.6, device="cuda")
+    sg = torch.full((B, 1, 1, 1, 1), 0.8, device="cuda")
+    x0, guided = O.cfg_x0(y, u, xt, al, sg, 7.5, rescale, return_guided=True)
+    x0r, gr = R.cfg_x0(y, u, xt, al, sg, 7.5, rescale, return_guided=True)
+    # the std ratio is rounded to fp16 on both sides; a 1-ulp difference of that scalar moves every element by <= 2^-11
+    assert_close(guided, gr, rel=1e-3, max_rel=2e-3, what="guided output")
+    assert rel_l2_f(x0, x0r) <= 1e-3
+    assert torch.equal(O.cfg_x0(y, u, xt, al, sg, 7.5, rescale), x0)
+
+
+def rel_l2_f(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
 # ---- CogVideoX DiT helpers -------------------------------------------------------------------------
 @pytest.mark.parametrize("rows,K,N,flags,extras", [(322, 3072, 3072, 0, "bias,cs,res"), (700, 320, 1280, 8, "bias"),
                                                    (226, 1024, 640, 8, "bias,cs,res")])

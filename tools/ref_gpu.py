@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--t", type=int, default=899)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-star", action="store_true", help="time the reference only (bench.py's gpu_reference block)")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -99,19 +100,21 @@ def main():
            "tf32": "off (cudnn.allow_tf32 = cuda.matmul.allow_tf32 = False)"}
 
     # ---- star_b200 ---------------------------------------------------------------------------------------------
-    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
-    with torch.device("meta"):
-        net = ControlledV2VUNet(**kw)
-    net.load_state_dict({k: v.to(torch.float16) for k, v in sd.items()}, assign=True)
-    net.eval()
-    with torch.no_grad():
-        o_star, ts = event_ms(lambda: net(x, t, y, hint=hint), 1, args.iters)
-    o_star = o_star.float()
-    res["star_ms_per_forward"] = ts
-    res["star_finite"] = bool(torch.isfinite(o_star).all())
-    print(f"star_b200: {min(ts):.1f} ms / forward (min of {ts})", flush=True)
-    del net
-    torch.cuda.empty_cache()
+    o_star, ts = None, None
+    if not args.no_star:
+        from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+        with torch.device("meta"):
+            net = ControlledV2VUNet(**kw)
+        net.load_state_dict({k: v.to(torch.float16) for k, v in sd.items()}, assign=True)
+        net.eval()
+        with torch.no_grad():
+            o_star, ts = event_ms(lambda: net(x, t, y, hint=hint), 1, args.iters)
+        o_star = o_star.float()
+        res["star_ms_per_forward"] = ts
+        res["star_finite"] = bool(torch.isfinite(o_star).all())
+        print(f"star_b200: {min(ts):.1f} ms / forward (min of {ts})", flush=True)
+        del net
+        torch.cuda.empty_cache()
 
     # ---- reference fp32 (oracle; TF32 off, exact attention) ---------------------------------------------------------
     o32 = None
@@ -139,17 +142,23 @@ def main():
     res["ref_fp16_peak_gb"] = torch.cuda.max_memory_allocated() / 1e9
     print(f"reference fp16 autocast: {min(ts16):.1f} ms / forward (min of {ts16}), peak {res['ref_fp16_peak_gb']:.1f} GB", flush=True)
 
-    res["speedup_star_vs_ref_fp16"] = min(ts16) / min(ts)
-    res["frames_per_s_50step_cfg2"] = {"star": F / (100 * min(ts) / 1e3), "reference_fp16": F / (100 * min(ts16) / 1e3)}
-    res["rel_l2"] = {"star_vs_ref_fp16": rel_l2(o_star, o16)}
-    res["max_abs_over_max"] = {"star_vs_ref_fp16": max_rel(o_star, o16)}
+    res["frames_per_s_50step_cfg2"] = {"reference_fp16": F / (100 * min(ts16) / 1e3)}
+    res["rel_l2"], res["max_abs_over_max"] = {}, {}
     if o32 is not None:
-        res["rel_l2"].update({"star_vs_ref_fp32": rel_l2(o_star, o32), "ref_fp16_vs_ref_fp32": rel_l2(o16, o32)})
-        res["max_abs_over_max"].update({"star_vs_ref_fp32": max_rel(o_star, o32), "ref_fp16_vs_ref_fp32": max_rel(o16, o32)})
+        res["rel_l2"]["ref_fp16_vs_ref_fp32"] = rel_l2(o16, o32)
+        res["max_abs_over_max"]["ref_fp16_vs_ref_fp32"] = max_rel(o16, o32)
+    if o_star is not None:
+        res["speedup_star_vs_ref_fp16"] = min(ts16) / min(ts)
+        res["frames_per_s_50step_cfg2"]["star"] = F / (100 * min(ts) / 1e3)
+        res["rel_l2"]["star_vs_ref_fp16"] = rel_l2(o_star, o16)
+        res["max_abs_over_max"]["star_vs_ref_fp16"] = max_rel(o_star, o16)
+        res["out_checksum"] = {"star_sum": float(o_star.double().sum()), "star_abs_mean": float(o_star.abs().mean())}
+    if o32 is not None and o_star is not None:
+        res["rel_l2"]["star_vs_ref_fp32"] = rel_l2(o_star, o32)
+        res["max_abs_over_max"]["star_vs_ref_fp32"] = max_rel(o_star, o32)
         # per-frame error of the star output (a >2^31-element indexing bug would show up as a bad frame range)
         pf = [(rel_l2(o_star[:, :, f], o32[:, :, f])) for f in range(F)]
         res["star_vs_ref_fp32_per_frame_minmax"] = [min(pf), max(pf)]
-    res["out_checksum"] = {"star_sum": float(o_star.double().sum()), "star_abs_mean": float(o_star.abs().mean())}
     print(json.dumps(res), flush=True)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
