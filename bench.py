@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--trace-out", default="", help="write the per-op time table of the timed region to this file")
     ap.add_argument("--no-vae", action="store_true", help="skip the (separately reported) VAE encode/decode legs")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; not a valid bench line)")
+    ap.add_argument("--workload", default="denoise", choices=["denoise", "vae", "cogvideox"],
+                    help="denoise = BASELINE config 2 (the driver's line); vae = config 5 decode sweep; cogvideox = config 4 DiT step")
+    ap.add_argument("--lib", default="", help="A/B: load this variant of libstar_sm100.so (tools/build_variant.py); not a valid bench line")
     return ap.parse_args()
 
 
@@ -335,10 +338,83 @@ def gpu_reference_block(H, W):
         return dict(note, unavailable=f"{type(e).__name__}: {str(e)[:200]}")
 
 
+# ---------------------------------------------------------------------------------- BASELINE config 5: VAE decode sweep
+# output size -> (latent h, latent w, analytic TFLOP per frame, analytic GB per frame)   SURVEY 8d / BASELINE.md 2 (GN+SiLU fused, fp16)
+VAE_SWEEP = {"540p/720p (720x1280)": (90, 160, 11.0, 17.2), "960p (976x1728)": (122, 216, 20.8, 31.5),
+             "1080p (1104x1984)": (138, 248, 27.5, 40.9)}
+
+
+def run_vae_sweep(args):
+    """Temporal-VAE decode of 3-frame windows (ref video_to_video_model.py:141-151) at the three BASELINE config-5 output
+    sizes, UNTILED: the largest window peaks at a few GB of the 180 GB HBM, so the reference's (non-existent) spatial tiling
+    is not needed on B200 and the per-window GroupNorm statistics stay exact by construction."""
+    from star_b200 import ops
+    from star_b200.utils.synth import synth_tensor
+    from star_b200.video_to_video.modules.temporal_vae import AutoencoderKLTemporalDecoder
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    with torch.device("meta"):
+        vae = AutoencoderKLTemporalDecoder()
+    vae.load_state_dict({k: synth_tensor(k, v.shape, 0, dev) for k, v in vae.state_dict().items()}, assign=True)
+    vae = vae.eval().requires_grad_(False)
+    peaks = measured_peaks()
+    rows = []
+    clocks = ClockSampler(0)
+    clocks.start()
+    n0 = ops.launch_count()
+    for name, (h, w, tflop, gb) in VAE_SWEEP.items():
+        z = torch.randn(3, 4, h, w, device=dev)
+        torch.cuda.reset_peak_memory_stats()
+        for _ in range(max(args.warmup, 1)):
+            out = vae.decode(z, num_frames=3).sample
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            out = vae.decode(z, num_frames=3).sample
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps / 3
+        ops.trace_begin()
+        vae.decode(z, num_frames=3)
+        agg = {}
+        for op, _sig, t_ms in ops.trace_end():
+            agg[op] = agg.get(op, 0.0) + t_ms
+        tot = sum(agg.values())
+        rows.append({"output": name, "latent": [h, w], "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
+                     "tflops": tflop / ms * 1e3 / 1e3, "tflops_frac_of_peak": tflop / ms / peaks["tflops"],
+                     "algorithmic_gb_per_s": gb / ms * 1e3, "hbm_frac_of_peak": gb / ms * 1e3 / peaks["hbm_gbs"],
+                     "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "finite": bool(torch.isfinite(out).all()),
+                     "op_share": {k: round(v / tot, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:5]}})
+    launches = ops.launch_count() - n0
+    mid = rows[1]
+    line = {"metric": "temporal-VAE decode frames/sec (3-frame windows), BASELINE config 5 sweep", "value": mid["frames_per_s"],
+            "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 3 * mid["ms_per_frame"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "VAE decode sweep 540p/720p/960p/1080p outputs (value = 976x1728), untiled 3-frame windows",
+                       "model": "AutoencoderKLTemporalDecoder (SVD temporal VAE), synthetic weights, PARITY UNPINNED (diffusers absent)",
+                       "l2": "activations (0.43 GB per 128-channel full-resolution tensor) exceed the 126 MB L2"},
+            "clocks": clocks.stop(), "gpu_launches": int(launches), "sweep": rows,
+            "roofline": {"kernel": "whole decode (conv / GroupNorm / conv_t3 kernels)", "bound": "hbm",
+                         "achieved": mid["algorithmic_gb_per_s"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": mid["hbm_frac_of_peak"], "traffic": None,
+                         "note": "algorithmic bytes assume GN+SiLU fused into the convs (SURVEY 8d); the unfused GroupNorm passes "
+                                 "move ~3x that, which is why TFLOP/s is the tighter bound today",
+                         "tensor_frac": mid["tflops_frac_of_peak"]}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "vae":
+        run_vae_sweep(args)
+        return
+    if args.workload == "cogvideox":
+        from tools.dit_bench import run_config4
+        run_config4(args)
         return
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -350,6 +426,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.lib:
+        import star_b200.lib as _lib
+        _lib.LIB_PATH = os.path.abspath(args.lib)
     from star_b200 import ops
     from star_b200.video_to_video.video_to_video_model import VideoToVideo_sr, make_chunks
 

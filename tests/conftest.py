@@ -18,6 +18,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (build container only)")
 
 
+def pytest_sessionstart(session):
+    # A/B experiments only (tools/build_variant.py): run the GPU suite against a variant library
+    variant = os.environ.get("STAR_LIB_VARIANT")
+    if variant:
+        import star_b200.lib as _lib
+        _lib.LIB_PATH = os.path.abspath(variant)
+        print(f"[conftest] using variant library {_lib.LIB_PATH}")
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()

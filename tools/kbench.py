@@ -10,6 +10,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if "--lib" in sys.argv:                       # A/B variant built by tools/build_variant.py
+    i = sys.argv.index("--lib")
+    import star_b200.lib as _lib
+    _lib.LIB_PATH = os.path.abspath(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
+    print("# library:", _lib.LIB_PATH)
 from star_b200 import ops as O  # noqa: E402
 
 PEAK = {"tflops": 1717.6, "gbs": 6576.1}
