@@ -382,7 +382,7 @@ def run_vae_sweep(args):
             agg[op] = agg.get(op, 0.0) + t_ms
         tot = sum(agg.values())
         rows.append({"output": name, "latent": [h, w], "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
-                     "tflops": tflop / ms * 1e3 / 1e3, "tflops_frac_of_peak": tflop / ms / peaks["tflops"],
+                     "tflops": tflop / ms * 1e3, "tflops_frac_of_peak": tflop / ms * 1e3 / peaks["tflops"],
                      "algorithmic_gb_per_s": gb / ms * 1e3, "hbm_frac_of_peak": gb / ms * 1e3 / peaks["hbm_gbs"],
                      "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "finite": bool(torch.isfinite(out).all()),
                      "op_share": {k: round(v / tot, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:5]}})

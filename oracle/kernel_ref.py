@@ -12,8 +12,14 @@ Never imported by the product.
 import torch
 import torch.nn.functional as F
 
-HALF = torch.float16
+HALF = torch.float16          # token dtype the references round to; tests of the bf16 library call set_dtype(torch.bfloat16)
 FLAG_GEGLU = 1
+
+
+def set_dtype(dtype):
+    global HALF
+    HALF = dtype
+
 FLAG_SILU_OUT = 2
 
 
@@ -185,7 +191,7 @@ def upsample2x_crop(x, BT, H, W):
     return up.reshape(-1, C).contiguous()
 
 
-def nchw5_to_tokens(x):
+def nchw5_to_tokens(x, dtype=None):
     B, C, Fr, H, W = x.shape
     return x.float().permute(0, 2, 3, 4, 1).reshape(B * Fr * H * W, C).to(HALF)
 
@@ -194,7 +200,7 @@ def tokens_to_nchw5(x, B, C, Fr, H, W):
     return x[:, :C].reshape(B, Fr, H, W, C).permute(0, 4, 1, 2, 3).contiguous()
 
 
-def sinusoidal(t, dim):
+def sinusoidal(t, dim, dtype=None):
     half = dim // 2
     tf = t.float()
     freqs = torch.pow(10000, -torch.arange(half, device=t.device).float().div(half))

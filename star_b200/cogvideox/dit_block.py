@@ -10,9 +10,10 @@ sat's default SelfAttention / MLP (transformer.py:35-119, :202-312).  Same kerne
   * LayerNorm + adaLN modulate as ONE LayerNorm launch per (sample, text|image) segment: the modulation is folded
     into the affine parameters, gamma' = gamma (1 + scale), beta' = beta (1 + scale) + shift,
   * spatial / temporal LIEM gates on the channels-last token matrix (no (b t) c h w <-> (b h w) t c reshuffles).
-Precision: fp16 storage, fp32 accumulation (the reference config runs bf16; a bf16 instantiation of the kernels is
-the next step -- see DESIGN.md).  The oracle for this block (oracle/cogvideox_ref.py) is PARITY-UNPINNED: sat is not
-in the reference tree.
+Precision: ``dtype`` = torch.bfloat16 (the reference config, cogvideox_5b_infer_sr.yaml:11; runs on libstar_sm100_bf16.so,
+the same kernel sources built with -DSTAR_BF16) or torch.float16; fp32 accumulation, statistics and softmax in both.
+Oracles: oracle/cogvideox_sat.py executes the reference's own transformer.py / dit_video_concat.py behind a shim of the
+un-vendored SwissArmyTransformer; oracle/cogvideox_ref.py is the older line-by-line restatement of one layer.
 """
 import torch
 
@@ -25,11 +26,13 @@ class DiTLayer:
     """Holds the packed fp16 weights of one layer; ``forward(hidden, emb)`` -> new hidden (fp16)."""
 
     def __init__(self, sd, hidden=3072, heads=48, text_length=226, frames=13, height=30, width=45,
-                 ln_eps=1e-5, qk_ln_eps=1e-6, cos=None, sin=None, device="cuda"):
+                 ln_eps=1e-5, qk_ln_eps=1e-6, cos=None, sin=None, device="cuda", dtype=HALF, time_embed_dim=512):
         self.d, self.heads, self.tl = hidden, heads, text_length
         self.T, self.H, self.W = frames, height, width
         self.ln_eps, self.qk_eps = ln_eps, qk_ln_eps
+        self.dt = dtype
         dev = torch.device(device)
+        HALF = dtype                                                             # noqa: N806  (token dtype of this layer)
 
         def h(k):
             return sd[k].detach().to(dev, HALF).contiguous()
@@ -57,8 +60,8 @@ class DiTLayer:
         for bi in range(B):
             for seg, (lo, hi) in enumerate(((0, tl), (tl, S))):
                 sc, sh = scale[seg][bi].float(), shift[seg][bi].float()
-                gp = (g * (1 + sc)).to(HALF)
-                bp = (b * (1 + sc) + sh).to(HALF)
+                gp = (g * (1 + sc)).to(self.dt)
+                bp = (b * (1 + sc) + sh).to(self.dt)
                 rows = slice(bi * S + lo, bi * S + hi)
                 out[rows] = ops.layernorm(x[rows], gp, bp, eps=self.ln_eps)
         return out
@@ -69,8 +72,8 @@ class DiTLayer:
         B, S, d = hidden.shape
         tl, T, H, W = self.tl, self.T, self.H, self.W
         assert S == tl + T * H * W and d == self.d
-        x = hidden.to(HALF).reshape(B * S, d).contiguous()
-        mod = ops.linear(ops.silu(emb.to(HALF).contiguous()), self.w_ada, self.b_ada)           # (B, 12 d)
+        x = hidden.to(self.dt).reshape(B * S, d).contiguous()
+        mod = ops.linear(ops.silu(emb.to(self.dt).contiguous()), self.w_ada, self.b_ada)           # (B, 12 d)
         (sh_msa, sc_msa, g_msa, sh_mlp, sc_mlp, g_mlp, tsh_msa, tsc_msa, tg_msa, tsh_mlp, tsc_mlp, tg_mlp) = mod.chunk(12, dim=1)
 
         # ---- attention branch

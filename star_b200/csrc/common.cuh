@@ -10,6 +10,26 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// One source, two builds: libstar_sm100.so computes on fp16 tokens, libstar_sm100_bf16.so (-DSTAR_BF16) on bf16 tokens
+// (the CogVideoX DiT runs bf16: cogvideox_5b_infer_sr.yaml:11).  Every storage-type conversion in the kernels goes through
+// the intrinsics re-pointed below; accumulation, statistics and softmax stay fp32 in both builds.
+#ifdef STAR_BF16
+#include <cuda_bf16.h>
+#define __half __nv_bfloat16
+#define __half2 __nv_bfloat162
+#define __float2half_rn __float2bfloat16_rn
+#define __half2float __bfloat162float
+#define __floats2half2_rn __floats2bfloat162_rn
+#define __half22float2 __bfloat1622float2
+#define STAR_UMMA_FMT 1u                                   /* tcgen05 kind::f16 A/B format: 1 = bf16 */
+#define STAR_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define STAR_MMA_SYNC_T "bf16"
+#else
+#define STAR_UMMA_FMT 0u                                   /* 0 = fp16 */
+#define STAR_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define STAR_MMA_SYNC_T "f16"
+#endif
+
 namespace star {
 
 #define STAR_DEVINL __device__ __forceinline__
@@ -148,11 +168,11 @@ STAR_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uin
 }
 
 // Instruction descriptor for kind::f16 (fp16 A/B, fp32 accumulate):
-//   [4,6) D fmt: 1 = f32   [7,10) A fmt: 0 = f16   [10,13) B fmt: 0 = f16
+//   [4,6) D fmt: 1 = f32   [7,10) A fmt: 0 = f16, 1 = bf16   [10,13) B fmt: same
 //   [15] A major (0 = K)   [16] B major (0 = K, 1 = MN)
 //   [17,23) N >> 3         [24,29) M >> 4
 STAR_DEVINL constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+    return (1u << 4) | (STAR_UMMA_FMT << 7) | (STAR_UMMA_FMT << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
            ((M >> 4) << 24);
 }
 

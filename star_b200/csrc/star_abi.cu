@@ -85,7 +85,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
         if (box[i] == 0 || box[i] > 256) return fail("tensor map box[%d]=%u out of range", i, box[i]);
     }
     if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = g_encode(m, STAR_TMAP_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -276,7 +276,11 @@ void best_box_2d(int H, int W, int* th, int* tw) {
 
 extern "C" {
 
+#ifdef STAR_BF16
+int star_version(void) { return 101; }     /* odd: bf16 build */
+#else
 int star_version(void) { return 100; }
+#endif
 const char* star_last_error(void) { return g_err.c_str(); }
 long long star_launch_count(void) { return g_launches.load(); }
 

@@ -13,6 +13,13 @@
 #include "common.cuh"
 #include "tapgemm.cuh"
 
+// Attribution experiments (tools/build_variant.py -DSTAR_GEMM_EXP=n; the shipped library is n = 0):
+//   1: the epilogue computes and stages but never issues its TMA stores      -> time without the store path
+//   2: the epilogue only drains TMEM (no bias / activation math, no staging)  -> time of loads + MMA alone
+#ifndef STAR_GEMM_EXP
+#define STAR_GEMM_EXP 0
+#endif
+
 namespace star {
 
 constexpr int TG2_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle; warps 4-11: epilogue (two warps per TMEM lane quadrant)
@@ -250,6 +257,15 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 float f[32];
                 tmem_ld32(t_row + c0, v);
                 const int n0 = n_base + c0;
+#if STAR_GEMM_EXP == 2
+                tmem_ld_wait();
+                if (c0 == last_c0) {
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                if (v[0] == 0x12345678u) out_row[0] = 1;          // keep the load alive
+                continue;
+#endif
                 if (geglu) {
                     uint32_t g[32];
                     tmem_ld32(t_row + (BN / 2) + c0, g);
@@ -347,7 +363,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
             fence_proxy_async_smem();
             epi_bar_sync();
-            if (leader) {
+            if (leader && STAR_GEMM_EXP == 0) {
 #pragma unroll 1
                 for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
                     if (n_base + pass0 + sb * 32 < p.N)

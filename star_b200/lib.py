@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstar_sm100.so")
+LIB_PATH = os.path.join(_HERE, "libstar_sm100.so")              # fp16 tokens (I2VGen-XL path, VAE)
+LIB_PATH_BF16 = os.path.join(_HERE, "libstar_sm100_bf16.so")    # the same sources built with -DSTAR_BF16 (CogVideoX DiT)
 
 _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
 
@@ -51,7 +52,7 @@ SIGNATURES = {
     "star_silu": (_i, [_p, _p, _ll, _p]),
 }
 
-_lib = None
+_libs = {}
 _inited = set()
 
 
@@ -59,35 +60,46 @@ class StarError(RuntimeError):
     pass
 
 
-def get_lib():
-    global _lib
-    if _lib is None:
-        if not os.path.isfile(LIB_PATH):
+def _key(dtype):
+    return "bf16" if dtype is not None and str(dtype).endswith("bfloat16") else "fp16"
+
+
+def get_lib(dtype=None):
+    """The kernel library for fp16 tokens (default) or bf16 tokens (dtype = torch.bfloat16)."""
+    key = _key(dtype)
+    lib = _libs.get(key)
+    if lib is None:
+        path = LIB_PATH_BF16 if key == "bf16" else LIB_PATH
+        if not os.path.isfile(path):
             raise StarError(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). star_b200 has no fallback compute path.")
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = lib
-    return _lib
+        _libs[key] = lib
+    return lib
 
 
-def last_error():
-    return get_lib().star_last_error().decode(errors="replace")
+def last_error(dtype=None):
+    return get_lib(dtype).star_last_error().decode(errors="replace")
 
 
-def ensure_init(device_index):
-    if device_index in _inited:
+def ensure_init(device_index, dtype=None):
+    key = (_key(dtype), device_index)
+    if key in _inited:
         return
-    rc = get_lib().star_init(int(device_index))
+    rc = get_lib(dtype).star_init(int(device_index))
     if rc != 0:
-        raise StarError("star_init failed: " + last_error())
-    _inited.add(device_index)
+        raise StarError("star_init failed: " + last_error(dtype))
+    _inited.add(key)
+
+
+_last = [None]
 
 
 def check(rc, what):
     if rc != 0:
-        raise StarError(f"{what}: {last_error()}")
+        raise StarError(f"{what}: {last_error(_last[0])}")

@@ -61,14 +61,33 @@ def _traced(fn):
 
 
 def launch_count():
-    """Kernels launched by libstar_sm100.so since load."""
-    return _L.get_lib().star_launch_count()
+    """Kernels launched by the star_b200 libraries since load."""
+    return sum(lib.star_launch_count() for lib in _L._libs.values()) if _L._libs else _L.get_lib().star_launch_count()
 
 
-def _dev(t):
+# Token dtype of the op in flight: fp16 (libstar_sm100.so) or bf16 (libstar_sm100_bf16.so, same sources).  Set by _dev() from
+# the op's first tensor (or its explicit ``dtype=``); every allocation and dtype check inside the op follows it.
+_cur = [torch.float16]
+
+
+def _dt():
+    return _cur[0]
+
+
+def _lib():
+    return _L.get_lib(_cur[0])
+
+
+def _dev(t, dtype=None):
     if not t.is_cuda:
         raise _L.StarError("star_b200 ops need CUDA tensors (no CPU fallback)")
-    _L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    if dtype is None:
+        dtype = t.dtype if t.dtype in (torch.float16, torch.bfloat16) else torch.float16
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise _L.StarError(f"star_b200 ops run on fp16 or bf16 tokens, not {dtype}")
+    _cur[0] = dtype
+    _L._last[0] = dtype
+    _L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device(), dtype)
     return t.device
 
 
@@ -81,8 +100,8 @@ def _st():
 
 
 def _h(t, name):
-    if t is not None and t.dtype != HALF:
-        raise _L.StarError(f"{name} must be fp16, got {t.dtype}")
+    if t is not None and t.dtype != _cur[0]:
+        raise _L.StarError(f"{name} must be {_cur[0]} like the op's first tensor, got {t.dtype}")
     return t
 
 
@@ -104,12 +123,12 @@ def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, o
     N = n_w // 2 if (flags & FLAG_GEGLU) else n_w
     assert w.is_contiguous() and w.shape[1] == K
     if out is None:
-        out = torch.empty((rows, N), dtype=HALF, device=a.device)
+        out = torch.empty((rows, N), dtype=_dt(), device=a.device)
     ldo = _rowmajor(out, "out")
     ldres = _rowmajor(residual, "residual") if residual is not None else 0
     if rowvec is not None:
         assert rowvec.is_contiguous() and rowvec.shape[-1] == N
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_linear(_p(a), lda, _p(w), _p(bias), _p(rowvec), int(rowvec_div), _p(residual), ldres,
                            _p(out), ldo, rows, K, N, flags, _st()), "star_linear")
     return out
@@ -123,10 +142,10 @@ def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=N
     Cout = w9.shape[0]
     assert x.is_contiguous() and w9.is_contiguous() and w9.shape[1:] == (3, 3, Cin)
     if out is None:
-        out = torch.empty((BT * H * W, Cout), dtype=HALF, device=x.device)
+        out = torch.empty((BT * H * W, Cout), dtype=_dt(), device=x.device)
     ldo = _rowmajor(out, "out")
     ldres = _rowmajor(residual, "residual") if residual is not None else 0
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_conv2d_3x3(_p(x), _p(w9), _p(bias), _p(rowvec), int(rowvec_div), _p(residual), ldres,
                                _p(out), ldo, BT, H, W, Cin, Cout, _st()), "star_conv2d_3x3")
     return out
@@ -140,9 +159,9 @@ def conv2d_3x3_s2(x, w9, bias=None):
     Cout = w9.shape[0]
     assert x.is_contiguous() and w9.is_contiguous()
     Ho, Wo = (H + 1) // 2 + 1, (W - 1) // 2 + 1
-    L = _L.get_lib()
+    L = _lib()
     ws = torch.empty(L.star_conv2d_s2_workspace_bytes(BT, H, W, Cin), dtype=torch.uint8, device=x.device)
-    out = torch.empty((BT * Ho * Wo, Cout), dtype=HALF, device=x.device)
+    out = torch.empty((BT * Ho * Wo, Cout), dtype=_dt(), device=x.device)
     _L.check(L.star_conv2d_3x3_s2(_p(x), _p(w9), _p(bias), _p(out), Cout, _p(ws), BT, H, W, Cin, Cout, _st()),
              "star_conv2d_3x3_s2")
     return out, Ho, Wo
@@ -157,9 +176,9 @@ def conv2d_3x3_s2p(x, w9, bias=None, pad=(0, 1, 0, 1)):
     assert x.is_contiguous() and w9.is_contiguous()
     pt, pb, pl, pr = (int(v) for v in pad)
     Ho, Wo = (H + pt + pb - 3) // 2 + 1, (W + pl + pr - 3) // 2 + 1
-    L = _L.get_lib()
+    L = _lib()
     ws = torch.empty(L.star_conv2d_s2p_workspace_bytes(BT, H, W, Cin, pt, pb, pl, pr), dtype=torch.uint8, device=x.device)
-    out = torch.empty((BT * Ho * Wo, Cout), dtype=HALF, device=x.device)
+    out = torch.empty((BT * Ho * Wo, Cout), dtype=_dt(), device=x.device)
     _L.check(L.star_conv2d_3x3_s2p(_p(x), _p(w9), _p(bias), _p(out), Cout, _p(ws), BT, H, W, Cin, Cout, pt, pb, pl, pr,
                                    _st()), "star_conv2d_3x3_s2p")
     return out, Ho, Wo
@@ -173,9 +192,9 @@ def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
     assert rows == B * T * HW and x.is_contiguous() and w3.is_contiguous()
     Cout = w3.shape[0]
     if out is None:
-        out = torch.empty((rows, Cout), dtype=HALF, device=x.device)
+        out = torch.empty((rows, Cout), dtype=_dt(), device=x.device)
     ldres = _rowmajor(residual, "residual") if residual is not None else 0
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_conv_t3(_p(x), _p(w3), _p(bias), _p(residual), ldres, _p(out), _rowmajor(out, "out"),
                             B, T, HW, Cin, Cout, _st()), "star_conv_t3")
     return out
@@ -188,8 +207,8 @@ def conv2d_3x3_c4(x, w9, bias=None, residual=None):
     BT, H, W, C = x.shape
     assert C == 4 and x.is_contiguous() and w9.is_contiguous()
     Cout = w9.shape[0]
-    out = torch.empty((BT * H * W, Cout), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((BT * H * W, Cout), dtype=_dt(), device=x.device)
+    L = _lib()
     ws = torch.empty(L.star_conv2d_c4_workspace_bytes(BT, H, W, Cout), dtype=torch.uint8, device=x.device)
     _L.check(L.star_conv2d_3x3_c4(_p(x), _p(w9), _p(bias), _p(residual), _p(out), _p(ws), BT, H, W, Cout, _st()),
              "star_conv2d_3x3_c4")
@@ -202,8 +221,8 @@ def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=No
     _dev(q)
     ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
     if out is None:
-        out = torch.empty((batch * Nq, heads * 64), dtype=HALF, device=q.device)
-    L = _L.get_lib()
+        out = torch.empty((batch * Nq, heads * 64), dtype=_dt(), device=q.device)
+    L = _lib()
     _L.check(L.star_attention(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), _rowmajor(out, "out"), batch, heads,
                               Nq, Nk, kv_batch_div, float(scale), _st()), "star_attention")
     return out
@@ -213,8 +232,8 @@ def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=No
 def temporal_attention(qkv, B, T, HW, heads, Ci, scale=0.125):
     _dev(qkv)
     ld = _rowmajor(qkv, "qkv")
-    out = torch.empty((qkv.shape[0], Ci), dtype=HALF, device=qkv.device)
-    L = _L.get_lib()
+    out = torch.empty((qkv.shape[0], Ci), dtype=_dt(), device=qkv.device)
+    L = _lib()
     _L.check(L.star_temporal_attention(_p(qkv), ld, _p(out), Ci, B, T, HW, heads, Ci, float(scale), _st()),
              "star_temporal_attention")
     return out
@@ -226,7 +245,7 @@ def groupnorm(x, gamma, beta, nsamples, eps, silu, out=None):
     _dev(x)
     rows, C = x.shape
     assert x.is_contiguous() and rows % nsamples == 0
-    L = _L.get_lib()
+    L = _lib()
     ws = torch.empty(L.star_groupnorm_workspace_bytes(nsamples, C), dtype=torch.uint8, device=x.device)
     if out is None:
         out = torch.empty_like(x)
@@ -242,7 +261,7 @@ def layernorm(x, gamma, beta, gate_mode=0, gate=None, w0=0.0, w1=0.0, eps=1e-5):
     rows, C = x.shape
     assert x.is_contiguous()
     out = torch.empty_like(x)
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), gate_mode, _p(gate),
                               float(w0), float(w1), _st()), "star_layernorm")
     return out
@@ -253,9 +272,9 @@ def liem_spatial_gate(x, w98, BT, H, W):
     _dev(x)
     rows, C = x.shape
     assert rows == BT * H * W and x.is_contiguous()
-    mm = torch.empty((rows, 2), dtype=HALF, device=x.device)
-    gate = torch.empty((rows,), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    mm = torch.empty((rows, 2), dtype=_dt(), device=x.device)
+    gate = torch.empty((rows,), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_liem_spatial_gate(_p(x), _p(w98), _p(mm), _p(gate), BT, H, W, C, _st()),
              "star_liem_spatial_gate")
     return gate
@@ -267,8 +286,8 @@ def concat_add(a, b, c=None):
     rows, Ca = a.shape
     Cb = b.shape[1]
     assert a.is_contiguous() and b.is_contiguous() and (c is None or c.is_contiguous())
-    out = torch.empty((rows, Ca + Cb), dtype=HALF, device=a.device)
-    L = _L.get_lib()
+    out = torch.empty((rows, Ca + Cb), dtype=_dt(), device=a.device)
+    L = _lib()
     _L.check(L.star_concat_add(_p(a), Ca, _p(b), _p(c), Cb, _p(out), rows, _st()), "star_concat_add")
     return out
 
@@ -278,7 +297,7 @@ def add(a, b):
     _dev(a)
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
     out = torch.empty_like(a)
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_add(_p(a), _p(b), _p(out), a.numel(), _st()), "star_add")
     return out
 
@@ -287,8 +306,8 @@ def add(a, b):
 def upsample2x_crop(x, BT, H, W):
     _dev(x)
     C = x.shape[1]
-    out = torch.empty((BT * (2 * H - 2) * (2 * W), C), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((BT * (2 * H - 2) * (2 * W), C), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_upsample2x_crop(_p(x), _p(out), BT, H, W, C, _st()), "star_upsample2x_crop")
     return out
 
@@ -299,8 +318,8 @@ def upsample2x(x, BT, H, W):
     _dev(x)
     C = x.shape[1]
     assert x.is_contiguous()
-    out = torch.empty((BT * 4 * H * W, C), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((BT * 4 * H * W, C), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_upsample2x(_p(x), _p(out), BT, H, W, C, 0, _st()), "star_upsample2x")
     return out
 
@@ -310,7 +329,7 @@ def softmax_rows(s, cols):
     """in-place row softmax of the fp16 matrix s[rows, ld] over its first `cols` columns"""
     _dev(s)
     ld = _rowmajor(s, "s")
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_softmax_rows(_p(s), ld, s.shape[0], int(cols), _st()), "star_softmax_rows")
     return s
 
@@ -321,21 +340,21 @@ def vae_head(x, w27, bias3, B, T, H, W):
     _dev(x)
     ld = _rowmajor(x, "x")
     assert w27.is_contiguous() and w27.numel() == 27 and bias3.numel() == 3
-    out = torch.empty((B * T, 3, H, W), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((B * T, 3, H, W), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_vae_head(_p(x), ld, _p(_h(w27, "w27")), _p(_h(bias3, "bias3")), _p(out), B, T, H * W, _st()),
              "star_vae_head")
     return out
 
 
 @_traced
-def nchw5_to_tokens(x):
-    """(b, c, f, h, w) fp32 -> [(b f h w), c] fp16"""
-    _dev(x)
+def nchw5_to_tokens(x, dtype=torch.float16):
+    """(b, c, f, h, w) fp32 -> [(b f h w), c] fp16 (or bf16)"""
+    _dev(x, dtype)
     x = x.contiguous().float()
     B, C, F, H, W = x.shape
-    out = torch.empty((B * F * H * W, C), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((B * F * H * W, C), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_nchw5_to_tokens(_p(x), _p(out), B, C, F, H * W, _st()), "star_nchw5_to_tokens")
     return out
 
@@ -343,18 +362,18 @@ def nchw5_to_tokens(x):
 @_traced
 def tokens_to_nchw5(x, B, C, F, H, W):
     _dev(x)
-    out = torch.empty((B, C, F, H, W), dtype=HALF, device=x.device)
-    L = _L.get_lib()
+    out = torch.empty((B, C, F, H, W), dtype=_dt(), device=x.device)
+    L = _lib()
     _L.check(L.star_tokens_to_nchw5(_p(x), _rowmajor(x, "x"), _p(out), B, C, F, H * W, _st()), "star_tokens_to_nchw5")
     return out
 
 
 @_traced
-def sinusoidal(t, dim):
-    _dev(t)
+def sinusoidal(t, dim, dtype=torch.float16):
+    _dev(t, dtype)
     t = t.to(torch.int64).contiguous()
-    out = torch.empty((t.shape[0], dim), dtype=HALF, device=t.device)
-    L = _L.get_lib()
+    out = torch.empty((t.shape[0], dim), dtype=_dt(), device=t.device)
+    L = _lib()
     _L.check(L.star_sinusoidal(_p(t), _p(out), t.shape[0], dim, _st()), "star_sinusoidal")
     return out
 
@@ -364,7 +383,7 @@ def silu(x):
     _dev(x)
     assert x.is_contiguous()
     out = torch.empty_like(x)
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_silu(_p(x), _p(out), x.numel(), _st()), "star_silu")
     return out
 
@@ -382,7 +401,7 @@ def bilinear_pad(x, H, W, padding=(0, 0, 0, 0), value=1.0):
     nc = 1
     for d in lead:
         nc *= d
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_bilinear_pad(_p(x), _p(out), nc, h, w, int(H), int(W), pl, pr, pt, pb, float(value), _st()),
              "star_bilinear_pad")
     return out
@@ -401,7 +420,7 @@ def cfg_x0(y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale=None, re
     guided = torch.empty_like(y_out) if return_guided else None
     al = alphas.reshape(B).float().contiguous()
     sg = sigmas.reshape(B).float().contiguous()
-    L = _L.get_lib()
+    L = _lib()
     ws = torch.empty(L.star_cfg_x0_workspace_bytes(B), dtype=torch.uint8, device=y_out.device)
     _L.check(L.star_cfg_x0(_p(y_out), _p(u_out), _p(xt), _p(x0), _p(guided), float(guide_scale),
                            -1.0 if guide_rescale is None else float(guide_rescale), _p(al), _p(sg), B, per, _p(ws), _st()),
@@ -421,9 +440,9 @@ def linear_ex(a, w, bias=None, colscale=None, residual=None, flags=0, out=None):
     N = w.shape[0]
     assert w.is_contiguous() and w.shape[1] == K
     if out is None:
-        out = torch.empty((rows, N), dtype=HALF, device=a.device)
+        out = torch.empty((rows, N), dtype=_dt(), device=a.device)
     ldres = _rowmajor(residual, "residual") if residual is not None else 0
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_linear_ex(_p(a), lda, _p(w), _p(bias), None, 1, _p(colscale), _p(residual), ldres, _p(out),
                               _rowmajor(out, "out"), rows, K, N, flags, _st()), "star_linear_ex")
     return out
@@ -436,7 +455,7 @@ def row_gate(x, mode, gate=None, w0=0.0, w1=0.0, out=None):
     assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_row_gate(_p(x), _p(out), rows, C, mode, _p(gate), float(w0), float(w1), _st()), "star_row_gate")
     return out
 
@@ -447,7 +466,7 @@ def qk_ln_rope(qkv, heads, koff, qg, qb, kg, kb, cos, sin, seq, text_len, eps=1e
     _dev(qkv)
     ld = _rowmajor(qkv, "qkv")
     assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
-    L = _L.get_lib()
+    L = _lib()
     _L.check(L.star_qk_ln_rope(_p(qkv), ld, qkv.shape[0], heads, koff, _p(qg), _p(qb), _p(kg), _p(kb), _p(cos), _p(sin),
                                seq, text_len, float(eps), _st()), "star_qk_ln_rope")
     return qkv

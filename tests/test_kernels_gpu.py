@@ -369,3 +369,44 @@ def test_vae_head_upsample_and_inplace_groupnorm(env):
     w9, b = rnd(3, 3, 3, 128, seed=9, scale=(9 * 128) ** -0.5), rnd(3, seed=10, scale=0.1)
     O.conv2d_3x3(xin, w9, b, out=rgb[:, :3])
     assert_close(rgb[:, :3], R.conv2d_3x3(xin, w9, b), what="conv 128->3 into ld=8 rows")
+
+
+# ---- bf16 build of the same kernels (libstar_sm100_bf16.so, -DSTAR_BF16): the CogVideoX DiT's dtype --------------------
+@pytest.fixture()
+def bf16_ref():
+    from oracle import kernel_ref as R
+    R.set_dtype(torch.bfloat16)
+    yield R
+    R.set_dtype(torch.float16)
+
+
+def test_bf16_library_kernels(env, bf16_ref):
+    """GEMM (+bias, residual, tanh-GELU, colscale), flash attention, LayerNorm, row gates, qk-LN + RoPE, SiLU on bf16 tokens
+    against the same torch references rounding to bf16 (8-bit mantissa: 8e-3 relative L2)."""
+    O, R = env[0], bf16_ref
+    bf = torch.bfloat16
+
+    def rb(*shape, seed=0, scale=1.0):
+        return rnd(*shape, seed=seed, scale=scale).to(bf)
+    a, w, bias, res = rb(1000, 3072, seed=1), rb(1536, 3072, seed=2, scale=3072 ** -0.5), rb(1536, seed=3, scale=0.1), rb(1000, 1536, seed=4)
+    assert_close(O.linear(a, w, bias, res), R.linear(a, w, bias, res), rel=8e-3, max_rel=5e-2, what="bf16 linear")
+    cs = rb(1536, seed=5)
+    assert_close(O.linear_ex(a, w, bias, cs, res, 8), R.linear_ex(a, w, bias, cs, res, 8), rel=8e-3, max_rel=5e-2, what="bf16 linear_ex")
+    qkv = rb(2 * 700, 3 * 256, seed=6)
+    got = O.attention(qkv[:, :256], qkv[:, 256:512], qkv[:, 512:], 2, 4, 700, 700, 1, 0.125)
+    assert got.dtype == bf
+    assert_close(got, R.attention(qkv[:, :256], qkv[:, 256:512], qkv[:, 512:], 2, 4, 700, 700, 1, 0.125), rel=8e-3, max_rel=5e-2,
+                 what="bf16 attention")
+    x = rb(500, 3072, seed=7)
+    g, b = (1 + 0.1 * torch.randn(3072, device="cuda")).to(bf), (0.1 * torch.randn(3072, device="cuda")).to(bf)
+    assert_close(O.layernorm(x, g, b), R.layernorm(x, g, b), rel=8e-3, max_rel=5e-2, what="bf16 layernorm")
+    assert_close(O.row_gate(x, 2, None, 0.4, -0.3), R.row_gate(x, 2, None, 0.4, -0.3), rel=8e-3, max_rel=5e-2, what="bf16 row_gate")
+    assert_close(O.silu(x), R.silu(x), rel=8e-3, max_rel=5e-2, what="bf16 silu")
+    t = torch.tensor([731, 12], device="cuda")
+    assert_close(O.sinusoidal(t, 3072, dtype=bf), R.sinusoidal(t, 3072), rel=8e-3, max_rel=5e-2, what="bf16 sinusoidal")
+    xi = rb(3 * 6 * 10, 256, seed=8)
+    w98 = rb(98, seed=9, scale=0.2)
+    assert_close(O.liem_spatial_gate(xi, w98, 3, 6, 10), R.liem_spatial_gate(xi, w98, 3, 6, 10), rel=1e-2, max_rel=5e-2, what="bf16 liem")
+    # the fp16 library is untouched by the switch
+    h = rnd(300, 320, seed=1)
+    assert O.linear(h, rnd(320, 320, seed=2, scale=0.05)).dtype == torch.float16

@@ -49,5 +49,129 @@ def main():
     print("  ops:", ", ".join(f"{k} {v:.2f} ms ({100 * v / tot:.0f}%)" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])))
 
 
+def run_config4(args):
+    """bench.py --workload cogvideox: BASELINE config 4 -- CogVideoX-5B heavy-deg 4x, 49 frames 720x480 (latent 13 x 60 x 90,
+    patch 2 -> 17 550 image + 226 text tokens), the whole 42-layer DiffusionTransformer with LoRA r = 512 merged, bf16 (the
+    reference's dtype), CFG pair as batch 2.  A "step" = one DiT forward of the CFG pair + guidance combine (the sampler's
+    elementwise update acts on a 1.4 MB latent)."""
+    import json
+    import torch.distributed as dist
+    from bench import ClockSampler, measured_peaks
+    from star_b200.cogvideox import DiffusionTransformer
+    from star_b200.utils.synth import synth_tensor
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16
+    layers = 4 if args.small else 42
+    with torch.device("meta"):
+        net = DiffusionTransformer(num_layers=layers, dtype=dtype)
+    sd = {}
+    for k, v in net.state_dict().items():
+        t = synth_tensor(k, v.shape, 7, dev)
+        sd[k] = t * (0.5 if "local.conv1" in k else 1.0)
+    net.load_state_dict(sd, assign=True)
+    net._pack()
+    del sd
+    for p in list(net.parameters()):                      # packed bf16 copies are what runs; drop the fp32 masters
+        p.data = torch.empty(0, device=dev)
+    torch.cuda.empty_cache()
+    T, H, W, tl = 13, 60, 90, 226
+    g = torch.Generator().manual_seed(0)
+    # CFG: split the pair across 2 ranks when available (the only parallel axis of one clip, SURVEY 8e); else batch 2
+    split = world >= 2
+    bsz = 1 if split else 2
+    x = torch.randn(2, T, 32, H, W, generator=g)
+    ctx = torch.randn(2, tl, 4096, generator=g)
+    x_pin, ctx_pin = x.pin_memory(), ctx.pin_memory()
+    lo = (rank % 2) if split else 0
+    xd, cd = x[lo:lo + bsz].to(dev), ctx[lo:lo + bsz].to(dev)
+    ts = torch.full((bsz,), 500, device=dev)
+
+    def step(xx, cc):
+        out = net(xx, timesteps=ts, context=cc).float()
+        if split:
+            both = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(both, out)
+            cond, unc = both[0], both[1]
+        else:
+            cond, unc = out[:1], out[1:]
+        return unc + 6.0 * (cond - unc)                         # DynamicCFG at its plateau (guiders.py:61-79)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 1)):
+        step(xd, cd)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = ops.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        out = step(xd, cd)
+    b.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    ms = a.elapsed_time(b) / args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step(x_pin[lo:lo + bsz].to(dev, non_blocking=True), ctx_pin[lo:lo + bsz].to(dev, non_blocking=True)).cpu()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt.tolist()
+    ops.trace_begin()
+    step(xd, cd)
+    trace = ops.trace_end()
+    att = [t_ms for name, sig, t_ms in trace if name == "attention"]
+    per_op = {}
+    for name, _sig, t_ms in trace:
+        per_op[name] = per_op.get(name, 0.0) + t_ms
+    peaks = measured_peaks()
+    S = tl + T * (H // 2) * (W // 2)
+    aflops = 4.0 * S * S * 64 * 48 * bsz
+    clips = (world // 2) if split else world                   # replicas beyond the CFG pair (different clips in production)
+    d, ff = 3072, 4 * 3072
+    layer_flops = 2 * (2.0 * S * d * 3 * d + 2.0 * S * d * d + 4.0 * S * d * ff) + 2 * 4.0 * S * S * d   # both CFG branches
+    if rank == 0:
+        line = {"metric": "upscaled frames/sec, CogVideoX-5B heavy-deg 4x, 49-frame 720x480, 50 steps", "value": 49.0 / (50 * ms / 1e3),
+                "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong" if split and world == 2 else "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE config 4: CogVideoX-5B DiT, 49 frames 720x480 (latent 13x60x90, 17 776 tokens), 50 steps, CFG pair",
+                           "model": f"DiffusionTransformer {layers} layers x 3072, 48 heads, LoRA r=512 merged, synthetic weights"
+                                    + (" (REDUCED DEPTH, debug)" if args.small else ""),
+                           "parallelism": "CFG pair split over 2 ranks, one all-gather of the 1.4 MB prediction per step" if split else "single GPU, CFG pair as batch 2",
+                           "step": "one DiT forward of the CFG pair + guidance combine",
+                           "l2": "activations (109 MB per 3072-wide token matrix per sample) exceed the L2 across a layer; no explicit flush"},
+                "clocks": clocks.stop(), "gpu_launches": int(launches),
+                "e2e": {"value": 49.0 / (50 * e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int((x[0].numel() + ctx[0].numel()) * 4 * bsz), "d2h_bytes_per_step": int(res.numel() * 4),
+                        "api": "DiffusionTransformer.forward(host tensors) + CFG combine, .cpu() per step"},
+                "roofline": {"kernel": "attn4_fwd_kernel (3-D full attention, 48 heads, N = 17 776)", "bound": "tensor",
+                             "achieved": aflops / (sum(att) / max(len(att), 1) * 1e-3) / 1e12 if att else None, "peak": peaks["tflops"],
+                             "unit": "TFLOP/s", "frac": (aflops / (sum(att) / max(len(att), 1) * 1e-3) / 1e12 / peaks["tflops"]) if att else None,
+                             "algorithmic_flops_per_launch": aflops, "launches_timed": len(att), "traffic": None},
+                "model_tflops_per_s": layers * layer_flops * (bsz / 2.0) / (ms * 1e-3) / 1e12,
+                "op_time_share": {k: round(v / sum(per_op.values()), 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
+                "out_checksum": {"finite": bool(torch.isfinite(out).all()), "abs_mean": float(out.abs().mean())},
+                "parity": "tests/test_cogvideox.py::test_dit_model_gpu_vs_reference_files (reference files behind the sat shim)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     main()
