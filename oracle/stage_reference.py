@@ -33,6 +33,7 @@ FILES = [
     "video_to_video/utils/seed.py",
     "cogvideox-based/transformer.py",
     "cogvideox-based/sat/dit_video_concat.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/util.py",
 ]
 
 

@@ -31,6 +31,9 @@ int g_sms[STAR_MAX_DEVICES] = {0};            // SM count per initialised device
 constexpr int kWideWastePct = 10;             // largest padding (percent of N) accepted for the 128x256 tiles ...
 constexpr int kWideWasteLongKPct = 25;        // ... and for reductions >= 1920 (N = 640 as 3 x 256: +16 % on the 640-channel convs)
 constexpr int kWideMinK = 256;                // smallest reduction length that takes the 128x256 tiles
+#ifndef STAR_GEMM_DBUF_MAXK
+#define STAR_GEMM_DBUF_MAXK 700               // 128x256-tile GEMMs with reductions up to this length use two output staging buffers
+#endif                                        // (A/B: profiles/r02_kbench_gemm_dbuf_ab.log -- qkv -5 %, 512->1536 -9 %, longer K / narrower tiles lose)
 std::atomic<long long> g_launches{0};
 
 // SM count of the CURRENT device (kernels are launched on the caller's current device / stream)
@@ -220,15 +223,24 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     unsigned long long ostr[5], rstr[5];
     strides(d.ldo, ostr);
     if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (d.residual && TapGemm2Smem<BN>::RES_TMA) {
+    // Output staging depth.  Short reductions are epilogue-bound (the main loop alone runs at 75-82 % of peak, the serialised
+    // store drain costs 25-30 %: profiles/r02_kbench_gemm_attribution.log) -> two staging buffers, one operand stage fewer.
+    ex.dbuf = (BN == 256 && (long long)d.ntaps * d.K <= STAR_GEMM_DBUF_MAXK) ? 1 : 0;
+    ex.res_direct = 0;
+    bool res_tma = d.residual && TapGemm2Smem<BN>::RES_TMA;
+    if (ex.dbuf && res_tma && TapGemm2Smem<BN>::stages(true, true) < 3) {          // BN = 160: no room for both -> direct residual loads
+        ex.res_direct = 1;
+        res_tma = false;
+    }
+    if (res_tma) {
         strides(d.ldres, rstr);
         if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
         tr = to;
     }
     const int grid = (int)std::min<long long>(total, num_sms());
-    ex.stages = TapGemm2Smem<BN>::stages(d.residual != nullptr);
-    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(d.residual != nullptr), st>>>(ta, tw, to, tr, p, ex);
+    ex.stages = TapGemm2Smem<BN>::stages(res_tma, ex.dbuf != 0);
+    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(res_tma, ex.dbuf != 0), st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
     return 0;
 }
@@ -300,9 +312,9 @@ static int star_init_on_current(int device) {
 #define STAR_SMEM_ATTR(kernel, bytes) STAR_CUDA((cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))))
     STAR_SMEM_ATTR(tapgemm_kernel<128>, TapGemmSmem<128>::TOTAL);
     STAR_SMEM_ATTR(tapgemm_kernel<160>, TapGemmSmem<160>::TOTAL);
-    STAR_SMEM_ATTR(tapgemm2_kernel<128>, std::max(TapGemm2Smem<128>::total(false), TapGemm2Smem<128>::total(true)));
-    STAR_SMEM_ATTR(tapgemm2_kernel<160>, std::max(TapGemm2Smem<160>::total(false), TapGemm2Smem<160>::total(true)));
-    STAR_SMEM_ATTR(tapgemm2_kernel<256>, std::max(TapGemm2Smem<256>::total(false), TapGemm2Smem<256>::total(true)));
+    STAR_SMEM_ATTR(tapgemm2_kernel<128>, 232448);
+    STAR_SMEM_ATTR(tapgemm2_kernel<160>, 232448);
+    STAR_SMEM_ATTR(tapgemm2_kernel<256>, 232448);
     STAR_SMEM_ATTR(attn_fwd_kernel<false>, AttnSmemT<false>::TOTAL);
     STAR_SMEM_ATTR(attn_fwd_kernel<true>, AttnSmemT<true>::TOTAL);
     STAR_SMEM_ATTR(attn4_fwd_kernel, Attn4Smem::TOTAL);

@@ -36,13 +36,13 @@ struct TapGemm2Smem {
     static constexpr bool RES_TMA = BN <= 160;
     static constexpr int OUT_BYTES = TG_BM * OUT_COLS * 2;            // OUT_COLS/32 sub-tiles of [128 rows x 64 B]
     static constexpr int BUDGET = 232448 - 1024 - 256;                // 227 KB minus alignment slack and barriers
-    // as many operand stages as fit beside the staging buffer (and the residual buffer when there is one)
-    static constexpr int stages(bool has_res) {
-        int n = (BUDGET - OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1)) / STAGE_BYTES;
+    // as many operand stages as fit beside the staging buffer(s) (and the residual buffer when it is TMA-prefetched)
+    static constexpr int stages(bool res_tma, bool dbuf = false) {
+        int n = (BUDGET - OUT_BYTES * ((dbuf ? 2 : 1) + (res_tma ? 1 : 0))) / STAGE_BYTES;
         return n > TG2_MAX_STAGES ? TG2_MAX_STAGES : n;
     }
-    static constexpr int total(bool has_res) {
-        return stages(has_res) * STAGE_BYTES + OUT_BYTES * ((has_res && RES_TMA) ? 2 : 1) + 256 + 1024;
+    static constexpr int total(bool res_tma, bool dbuf = false) {
+        return stages(res_tma, dbuf) * STAGE_BYTES + OUT_BYTES * ((dbuf ? 2 : 1) + (res_tma ? 1 : 0)) + 256 + 1024;
     }
 };
 
@@ -53,13 +53,18 @@ STAR_DEVINL void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int
 }
 STAR_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+STAR_DEVINL void tma_store_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 STAR_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 STAR_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct TapGemm2Extra {
     int num_tiles;        // m_tiles * n_tiles
     int n_tiles;
-    int stages;           // operand ring depth (depends on BN and on whether a residual buffer is needed)
+    int stages;           // operand ring depth (depends on BN, the residual buffer and the staging depth)
+    int dbuf;             // 1: two output staging buffers -- the TMA-store drain of pass i overlaps the arithmetic of pass i+1
+                          //    (attribution, profiles/r02_kbench_gemm_attribution.log: with one buffer the short-K GEMMs lose
+                          //    25-30 % to the serialised drain)
+    int res_direct;       // 1: read the residual with direct 16-byte loads even where this BN would prefetch it by TMA
 };
 
 template <int BN>
@@ -74,9 +79,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int NS = ex.stages;
     const int OFF_OUT = NS * SM::STAGE_BYTES;
-    const int OFF_RES = OFF_OUT + SM::OUT_BYTES;
-    const bool res_tma = SM::RES_TMA && p.residual != nullptr;         // residual tile prefetched by TMA (else: direct loads)
-    const int OFF_BAR = OFF_OUT + SM::OUT_BYTES * (res_tma ? 2 : 1);
+    const int OFF_RES = OFF_OUT + SM::OUT_BYTES * (ex.dbuf ? 2 : 1);
+    const bool res_tma = SM::RES_TMA && p.residual != nullptr && !ex.res_direct;   // residual tile prefetched by TMA (else: direct loads)
+    const int OFF_BAR = OFF_RES + (res_tma ? SM::OUT_BYTES : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + TG2_MAX_STAGES;
     uint64_t* acc_full = empty_bar + TG2_MAX_STAGES; // 2
@@ -211,10 +216,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int swz = (r >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
-        uint8_t* out_row = smem + OFF_OUT + r * 64;
+        uint8_t* out_row0 = smem + OFF_OUT + r * 64;
         const uint8_t* res_row = smem + OFF_RES + r * 64;
         const bool leader = (threadIdx.x == 4 * 32);
         int local = 0;
+        int pass_ctr = 0;
         for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
             int org[4], n_tile;
             tile_origin(tile, org, n_tile);
@@ -247,8 +253,15 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             constexpr int PASS_COLS = SM::OUT_COLS;
 #pragma unroll 1
             for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS) {
-            // the TMA stores of the previous pass / tile must have finished reading the staging buffer
-            if (leader) tma_store_wait_read();
+            // the TMA stores that last used this staging buffer must have finished reading it: the previous pass with one
+            // buffer, the pass before the previous one with two
+            const int ob = ex.dbuf ? (pass_ctr & 1) : 0;
+            ++pass_ctr;
+            uint8_t* out_row = out_row0 + ob * SM::OUT_BYTES;
+            if (leader) {
+                if (ex.dbuf) tma_store_wait_read_but_one();
+                else tma_store_wait_read();
+            }
             epi_bar_sync();
             const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
 #pragma unroll 1
@@ -367,7 +380,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll 1
                 for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
                     if (n_base + pass0 + sb * 32 < p.N)
-                        tma_store_5d(&tmap_out, smem + OFF_OUT + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
+                        tma_store_5d(&tmap_out, smem + OFF_OUT + ob * SM::OUT_BYTES + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
                 }
                 tma_store_commit();
             }
