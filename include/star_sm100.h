@@ -136,6 +136,13 @@ int star_tokens_to_nchw5(const void* x, long long ldx, void* out, int B, int C, 
  * (video_to_video_model.py:81,:86-87): x fp32 (NC, h, w) -> out fp32 (NC, H + pad_t + pad_b, W + pad_l + pad_r). */
 int star_bilinear_pad(const void* x_f32, void* out_f32, long long NC, int h, int w, int H, int W, int pad_l, int pad_r,
                       int pad_t, int pad_b, float pad_value, void* stream);
+/* tensor2vid + adain_color_fix (inference_utils.py:16-23, video_super_resolution/color_fix.py:15-29,47-74): per frame and channel
+ * t = clamp((video + 1) / 2, 0, 1) is re-normalised to the mean / std (unbiased var + 1e-5) of s = (source + 1) / 2, clamped to [0, 1]
+ * and written * 255 as (F, H*W, C).  video fp32 (C, F, HW) = test()'s (1, C, F, H, W); source fp32 (F, C, src_hw) = the LR clip.
+ * Exactly one of out_f32 / out_u8 (rounded) is written.  workspace: star_adain_workspace_bytes(C, F). */
+long long star_adain_workspace_bytes(int C, int F);
+int star_adain_color_fix(const void* video_f32, const void* source_f32, void* out_f32, void* out_u8, int C, int F, long long HW,
+                         long long src_hw, void* workspace, void* stream);
 /* Classifier-free guidance + std-ratio rescale + v -> x0 (diffusion_sdedit.py:89-99) in two launches:
  *   out = u + g (y - u)   (fp16, each op rounded like the reference's fp16 tensor arithmetic)
  *   out *= r * std(y) / (std(out) + 1e-12) + (1 - r)      per sample over `per_sample` elements; r < 0: no rescale

@@ -304,3 +304,19 @@ def cfg_x0(y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale=None, re
         out = out * (guide_rescale * ratio + (1 - guide_rescale) * 1.0)
     x0 = alphas * xt - sigmas * out
     return (x0, out) if return_guided else x0
+
+
+def adain_color_fix(video, source, uint8=False):
+    """inference_utils.tensor2vid followed by color_fix.adain_color_fix, op by op (inference_sr.py:77-80)"""
+    v = (video.clone() * 0.5 + 0.5).clamp(0, 1) * 255.0                          # tensor2vid
+    target = v[0].permute(1, 2, 3, 0)                                             # b c f h w -> f h w c
+    target = target.permute(0, 3, 1, 2) / 255                                     # T H W C -> T C H W
+    src = (source.to(video.device) + 1) / 2
+    outs = []
+    for i in range(target.shape[0]):
+        c, s = target[i:i + 1], src[i:i + 1]
+        cm, cs = c.reshape(1, c.shape[1], -1).mean(2).reshape(1, -1, 1, 1), (c.reshape(1, c.shape[1], -1).var(2) + 1e-5).sqrt().reshape(1, -1, 1, 1)
+        sm, ss = s.reshape(1, s.shape[1], -1).mean(2).reshape(1, -1, 1, 1), (s.reshape(1, s.shape[1], -1).var(2) + 1e-5).sqrt().reshape(1, -1, 1, 1)
+        outs.append((c - cm) / cs * ss + sm)
+    res = torch.cat(outs).clamp_(0.0, 1.0).permute(0, 2, 3, 1) * 255
+    return res.round().to(torch.uint8) if uint8 else res

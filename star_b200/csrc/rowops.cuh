@@ -898,6 +898,61 @@ bilinear_pad_kernel(const float* __restrict__ x, float* __restrict__ out, long l
     }
 }
 
+// ------------------------------------------------------------------ post-processing (inference_utils.py:16-23, color_fix.py:15-74)
+// tensor2vid + adain_color_fix on the GPU: per (frame, channel) the SR frame t = clamp((x + 1) / 2, 0, 1) is re-normalised to the
+// mean / std of the LR frame s = (src + 1) / 2 (unbiased variance + 1e-5, like calc_mean_std) and written as (T, H, W, C) * 255.
+// Stage 1: sum / sum of squares of one tensor's planes into stats[plane][2] (double atomics); `clamp01` applies tensor2vid's clamp.
+__global__ void __launch_bounds__(256)
+plane_stats_kernel(const float* __restrict__ x, long long plane_elems, int clamp01, double* __restrict__ stats) {
+    const float* p = x + (long long)blockIdx.y * plane_elems;
+    float s = 0.f, ss = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane_elems; i += (long long)gridDim.x * blockDim.x) {
+        float v = __fmaf_rn(p[i], 0.5f, 0.5f);
+        if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+        s += v;
+        ss = fmaf(v, v, ss);
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    __shared__ float red[2][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double acc = 0.0;
+        for (int k = 0; k < 8; ++k) acc += (double)red[threadIdx.x][k];
+        atomicAdd(&stats[blockIdx.y * 2 + threadIdx.x], acc);
+    }
+}
+
+// Stage 2: video (C, F, H*W) fp32 in [-1, 1] -> out (F, H*W, C) fp32 in [0, 255] (or uint8 when out_u8 != nullptr).
+// tgt_stats planes are ordered (c, f) like the video, src_stats planes (f, c) like the LR clip (F, C, h, w).
+__global__ void __launch_bounds__(256)
+adain_apply_kernel(const float* __restrict__ video, float* __restrict__ out_f32, unsigned char* __restrict__ out_u8, int C, int F,
+                   long long HW, long long src_hw, const double* __restrict__ tgt_stats, const double* __restrict__ src_stats) {
+    const int f = blockIdx.y;
+    float scale[4], shift[4];
+    for (int c = 0; c < C && c < 4; ++c) {
+        const double nt = (double)HW, ns = (double)src_hw;
+        const double tm = tgt_stats[(c * F + f) * 2] / nt, sm = src_stats[(f * C + c) * 2] / ns;
+        const double tv = (tgt_stats[(c * F + f) * 2 + 1] - nt * tm * tm) / (nt - 1.0) + 1e-5;
+        const double sv = (src_stats[(f * C + c) * 2 + 1] - ns * sm * sm) / (ns - 1.0) + 1e-5;
+        const double k = sqrt(sv > 0 ? sv : 0.0) / sqrt(tv);
+        scale[c] = (float)k;
+        shift[c] = (float)(sm - tm * k);
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        for (int c = 0; c < C && c < 4; ++c) {
+            float v = __fmaf_rn(video[((long long)c * F + f) * HW + i], 0.5f, 0.5f);
+            v = fminf(fmaxf(v, 0.f), 1.f);
+            v = fminf(fmaxf(fmaf(v, scale[c], shift[c]), 0.f), 1.f) * 255.f;
+            const long long o = ((long long)f * HW + i) * C + c;
+            if (out_u8) out_u8[o] = (unsigned char)__float2int_rn(v);
+            else out_f32[o] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ guided x0 (diffusion_sdedit.py:89-99)
 // out = u + g (y - u) in fp16 (each op rounded like the reference's fp16 tensor ops), std-ratio rescale
 // out *= r * std(y) / (std(out) + 1e-12) + (1 - r) with per-sample (unbiased) std over the whole chunk, then

@@ -740,6 +740,28 @@ int star_bilinear_pad(const void* x_f32, void* out_f32, long long NC, int h, int
     return 0;
 }
 
+long long star_adain_workspace_bytes(int C, int F) { return (long long)C * F * 2 * 2 * 8; }
+
+int star_adain_color_fix(const void* video_f32, const void* source_f32, void* out_f32, void* out_u8, int C, int F, long long HW,
+                         long long src_hw, void* workspace, void* stream) {
+    if (C < 1 || C > 4 || F < 1 || HW < 2 || src_hw < 2) return fail("star_adain_color_fix: bad geometry (C <= 4)");
+    if ((out_f32 == nullptr) == (out_u8 == nullptr)) return fail("star_adain_color_fix: pass exactly one of out_f32 / out_u8");
+    if (F > 65535) return fail("star_adain_color_fix: too many frames");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* tgt = (double*)workspace;
+    double* src = tgt + (size_t)C * F * 2;
+    STAR_CUDA(cudaMemsetAsync(workspace, 0, (size_t)star_adain_workspace_bytes(C, F), st));
+    const unsigned gt = (unsigned)std::min<long long>((HW + 255) / 256, 256), gs = (unsigned)std::min<long long>((src_hw + 255) / 256, 256);
+    plane_stats_kernel<<<dim3(gt, C * F), 256, 0, st>>>((const float*)video_f32, HW, 1, tgt);
+    STAR_LAUNCH_CHECK("plane_stats(target)");
+    plane_stats_kernel<<<dim3(gs, C * F), 256, 0, st>>>((const float*)source_f32, src_hw, 0, src);
+    STAR_LAUNCH_CHECK("plane_stats(source)");
+    adain_apply_kernel<<<dim3((unsigned)std::min<long long>((HW + 255) / 256, 1024), F), 256, 0, st>>>(
+        (const float*)video_f32, (float*)out_f32, (unsigned char*)out_u8, C, F, HW, src_hw, tgt, src);
+    STAR_LAUNCH_CHECK("adain_apply");
+    return 0;
+}
+
 long long star_cfg_x0_workspace_bytes(int samples) { return (long long)samples * 4 * 8; }
 
 int star_cfg_x0(const void* y_out, const void* u_out, const void* xt_f32, void* x0_f32, void* guided_out,

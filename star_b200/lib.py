@@ -46,6 +46,8 @@ SIGNATURES = {
     "star_nchw5_to_tokens": (_i, [_p, _p, _i, _i, _i, _ll, _p]),
     "star_tokens_to_nchw5": (_i, [_p, _ll, _p, _i, _i, _i, _ll, _p]),
     "star_bilinear_pad": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "star_adain_workspace_bytes": (_ll, [_i, _i]),
+    "star_adain_color_fix": (_i, [_p, _p, _p, _p, _i, _i, _ll, _ll, _p, _p]),
     "star_cfg_x0_workspace_bytes": (_ll, [_i]),
     "star_cfg_x0": (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _ll, _p, _p]),
     "star_sinusoidal": (_i, [_p, _p, _i, _i, _p]),

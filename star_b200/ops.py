@@ -408,6 +408,23 @@ def bilinear_pad(x, H, W, padding=(0, 0, 0, 0), value=1.0):
 
 
 @_traced
+def adain_color_fix(video, source, uint8=False):
+    """tensor2vid + adain_color_fix on the GPU: video (1, C, F, H, W) fp32 in [-1, 1] (test()'s result), source (F, C, h, w) fp32 in
+    [-1, 1] (the LR clip) -> (F, H, W, C) in [0, 255], fp32 like the reference or uint8 (rounded; 4x less D2H traffic)."""
+    _dev(video)
+    assert video.dim() == 5 and video.shape[0] == 1 and video.dtype == torch.float32 and source.dtype == torch.float32
+    _, C, F, H, W = video.shape
+    assert source.shape[0] == F and source.shape[1] == C
+    video, source = video.contiguous(), source.to(video.device).contiguous()
+    out = torch.empty((F, H, W, C), dtype=torch.uint8 if uint8 else torch.float32, device=video.device)
+    L = _lib()
+    ws = torch.empty(L.star_adain_workspace_bytes(C, F), dtype=torch.uint8, device=video.device)
+    _L.check(L.star_adain_color_fix(_p(video), _p(source), None if uint8 else _p(out), _p(out) if uint8 else None, C, F, H * W,
+                                    source.shape[2] * source.shape[3], _p(ws), _st()), "star_adain_color_fix")
+    return out
+
+
+@_traced
 def cfg_x0(y_out, u_out, xt, alphas, sigmas, guide_scale, guide_rescale=None, return_guided=False):
     """x0 = alphas * xt - sigmas * rescale(u + g (y - u)); y_out / u_out fp16 (B, ...), xt fp32, alphas / sigmas fp32 (B, 1, ...)"""
     _dev(y_out)

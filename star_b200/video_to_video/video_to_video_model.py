@@ -134,7 +134,7 @@ class VideoToVideo_sr():
         negative_y = (self.negative_y if negative_y is None else negative_y).to(self.device)
         frames_num = feat.shape[2]
         t = torch.LongTensor([total_noise_levels - 1]).to(self.device)
-        noised_lr = self.diffusion.diffuse(feat, t, noise=noise)
+        noised_lr = self.diffusion.diffuse(feat, t, noise=noise).contiguous()
         if noise is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             torch.distributed.broadcast(noised_lr, 0)       # chunk-parallel ranks start from the same sample
@@ -156,13 +156,28 @@ class VideoToVideo_sr():
             return x.to(self.device, torch.float32)
         bounds = _shard_bounds(x.shape[dim], world)
         lo, hi = bounds[rank]
-        local = x.narrow(dim, lo, hi - lo).to(self.device, torch.float32, non_blocking=True)
+        local = x.narrow(dim, lo, hi - lo).contiguous().to(self.device, torch.float32)
         return _all_gather_varlen(local, [b - a for a, b in bounds], dim)
 
     # -- pixel-space entry (ref :75-139) ------------------------------------------------------------
     @torch.no_grad()
     def test(self, input: Dict[str, Any], total_noise_levels=1000, steps=50, solver_mode='fast', guide_scale=7.5,
              max_chunk_len=32):
+        """The reference entry (ref :75-139): (1, 3, F, H, W) fp32 on the CPU."""
+        return self._test_on_device(input, total_noise_levels, steps, solver_mode, guide_scale, max_chunk_len).type(torch.float32).cpu()
+
+    @torch.no_grad()
+    def enhance_frames(self, input: Dict[str, Any], total_noise_levels=1000, steps=50, solver_mode='fast', guide_scale=7.5,
+                       max_chunk_len=32, uint8=True):
+        """test() + the CLI's post-processing (inference_sr.py:77-80: tensor2vid, adain_color_fix against the LR clip) with the
+        post-processing on the GPU: returns (F, H, W, 3) frames in [0, 255] on the CPU -- uint8 by default, i.e. a quarter of the
+        device->host traffic of test()'s fp32 tensor."""
+        vid = self._test_on_device(input, total_noise_levels, steps, solver_mode, guide_scale, max_chunk_len).float()
+        if vid.is_cuda:
+            return ops.adain_color_fix(vid, input['video_data'].to(vid.device).float(), uint8=uint8).cpu()
+        raise NotImplementedError("enhance_frames runs the GPU post-processing kernels; use test() + the reference's CPU helpers otherwise")
+
+    def _test_on_device(self, input, total_noise_levels, steps, solver_mode, guide_scale, max_chunk_len):
         video_data = input['video_data']
         y = input['y']
         (target_h, target_w) = input['target_res']
@@ -197,8 +212,7 @@ class VideoToVideo_sr():
             else:
                 vid_tensor_gen = self._decode_sharded(gen_vid, 3, (h1, h + h1, w1, w + w1))
         logger.info('temporal vae decoding, finished.')
-        gen_video = rearrange(vid_tensor_gen, '(b f) c h w -> b c f h w', b=bs)
-        return gen_video.type(torch.float32).cpu()
+        return rearrange(vid_tensor_gen, '(b f) c h w -> b c f h w', b=bs)
 
     def upsample_pad(self, frames, target_h, target_w, padding):
         """(f,3,h,w) -> bilinear resize to (target_h, target_w) (F.interpolate semantics, align_corners=False) and

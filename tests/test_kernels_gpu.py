@@ -257,6 +257,18 @@ def test_cfg_x0(env, B, shape, rescale):
     assert torch.equal(O.cfg_x0(y, u, xt, al, sg, 7.5, rescale), x0)
 
 
+def test_adain_color_fix(env):
+    """tensor2vid + adain_color_fix (inference_utils.py:16-23, color_fix.py:15-74) as three launches"""
+    O, R = env
+    video = (torch.randn(1, 3, 4, 96, 128, device="cuda") * 0.8).contiguous()
+    src = torch.rand(4, 3, 24, 32, device="cuda") * 2 - 1
+    got, ref = O.adain_color_fix(video, src), R.adain_color_fix(video, src)
+    assert got.shape == ref.shape == (4, 96, 128, 3)
+    assert (got - ref).abs().max().item() <= 2e-2                   # on a 0..255 scale
+    g8, r8 = O.adain_color_fix(video, src, uint8=True), R.adain_color_fix(video, src, uint8=True)
+    assert g8.dtype == torch.uint8 and (g8.int() - r8.int()).abs().max().item() <= 1
+
+
 def rel_l2_f(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm()).item()
 

@@ -217,6 +217,13 @@ def test_pixel_pipeline_gpu():
         ref = oracle.test(inp, **kw)
     err = rel_l2(out, ref)
     print(f"pixel pipeline (4 frames, 64x96 -> 128x192, 4 solver steps, CFG 7.5): rel-L2 vs the fp32 oracle pipeline {err:.3e}")
+    # test() + the CLI's tensor2vid / adain_color_fix with the post-processing on the GPU (uint8 frames back)
+    from oracle import kernel_ref as KR
+    setup_seed(666)
+    frames = star.enhance_frames(inp, **kw)
+    want = KR.adain_color_fix(out, video, uint8=True)
+    assert frames.shape == (4, 128, 192, 3) and frames.dtype == torch.uint8 and frames.device.type == "cpu"
+    assert (frames.int() - want.int()).abs().max().item() <= 1
     assert err <= 3e-2              # CFG 7.5 amplifies the two branches' fp16 error over the solver steps; layout / window / crop bugs give O(1)
 
 
