@@ -48,7 +48,7 @@ int star_linear_ex(const void* A, long long lda, const void* W, const void* bias
 
 /* Conv2d 3x3 stride 1 pad 1 on X[BT,H,W,Cin]; W9 = weight permuted to [Cout][3][3][Cin]; rowvec = per-clip time
  * embedding added before the next GroupNorm; replaces cuDNN at unet_v2v.py:612,:639,:553-554,:1552. */
-int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div,
+int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div, long long ldrowvec,
                     const void* residual, long long ldres, void* out, long long ldo, int BT, int H, int W, int Cin,
                     int Cout, void* stream);
 /* Downsample: Conv2d 3x3 stride 2 padding (2,1) (unet_v2v.py:709-729).  Ho = (H+1)/2 + 1, Wo = (W-1)/2 + 1.

@@ -111,7 +111,7 @@ struct TapDesc {
     int tap[TG_MAX_TAPS][4];
     int K, N, flags;
     const void *W, *bias, *rowvec, *residual, *colscale;
-    long long rowvec_div, ldres, ldo;
+    long long rowvec_div, ldrowvec, ldres, ldo;
     void* out;
 };
 
@@ -139,6 +139,7 @@ int launch_tapgemm_bn(const TapDesc& d, cudaStream_t st) {
     p.bias = (const __half*)d.bias;
     p.rowvec = (const __half*)d.rowvec;
     p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
+    p.rowvec_ld = d.ldrowvec > 0 ? d.ldrowvec : d.N;
     p.residual = (const __half*)d.residual;
     p.res_ld = d.ldres;
     p.out = (__half*)d.out;
@@ -188,6 +189,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     p.bias = (const __half*)d.bias;
     p.rowvec = (const __half*)d.rowvec;
     p.rowvec_div = (int)std::max(1ll, d.rowvec_div);
+    p.rowvec_ld = d.ldrowvec > 0 ? d.ldrowvec : d.N;
     p.residual = (const __half*)d.residual;
     p.colscale = (const __half*)d.colscale;
     p.res_ld = d.ldres;
@@ -366,7 +368,7 @@ int star_linear_ex(const void* A, long long lda, const void* W, const void* bias
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
 
-int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div,
+int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void* rowvec, long long rowvec_div, long long ldrowvec,
                     const void* residual, long long ldres, void* out, long long ldo, int BT, int H, int W, int Cin,
                     int Cout, void* stream) {
     STAR_CHECK_INIT();
@@ -388,7 +390,8 @@ int star_conv2d_3x3(const void* X, const void* W9, const void* bias, const void*
             d.tap[r * 3 + s][1] = r - 1;
         }
     d.K = Cin; d.N = Cout;
-    d.W = W9; d.bias = bias; d.rowvec = rowvec; d.rowvec_div = rowvec_div; d.residual = residual; d.ldres = ldres;
+    d.W = W9; d.bias = bias; d.rowvec = rowvec; d.rowvec_div = rowvec_div; d.ldrowvec = ldrowvec; d.residual = residual; d.ldres = ldres;
+    if (rowvec && ldrowvec % 8) return fail("star_conv2d_3x3: ldrowvec must be a multiple of 8");
     d.out = out; d.ldo = ldo;
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
@@ -785,6 +788,18 @@ int star_cfg_x0(const void* y_out, const void* u_out, const void* xt_f32, void* 
     STAR_LAUNCH_CHECK("cfg_x0");
     return 0;
 }
+
+#if STAR_GEMM_TRACE
+// experiment builds only (tools/gemm_trace.py): copy CTA 0's role timelines to the host and reset them
+int star_debug_read_trace(long long* host_dst, int* host_counts) {
+    STAR_CUDA(cudaDeviceSynchronize());
+    STAR_CUDA(cudaMemcpyFromSymbol(host_dst, g_tg2_trace, sizeof(long long) * 3 * 4096));
+    STAR_CUDA(cudaMemcpyFromSymbol(host_counts, g_tg2_trace_n, sizeof(int) * 3));
+    int zero[3] = {0, 0, 0};
+    STAR_CUDA(cudaMemcpyToSymbol(g_tg2_trace_n, zero, sizeof(zero)));
+    return 0;
+}
+#endif
 
 int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream) {
     const int n = B * (dim / 2);

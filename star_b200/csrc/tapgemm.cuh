@@ -46,6 +46,7 @@ struct TapGemmParams {
     const __half* bias;   // [N] ([2N] with GEGLU) or null
     const __half* rowvec; // [rows_out / rowvec_div, N] or null  (time-embedding add, unet_v2v.py:684)
     int rowvec_div;
+    long long rowvec_ld;  // row pitch of rowvec in elements (>= N)
     const __half* colscale;   // [N] or null: acc = colscale[n] * (acc + bias[n]) before the residual add (adaLN gate)
     const __half* residual;   // [rows_out, res_ld] or null
     long long res_ld;
@@ -181,7 +182,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
         __half* out_row = p.out + orow * p.out_ld;
         const __half* res_row = p.residual ? p.residual + orow * p.res_ld : nullptr;
-        const __half* rv_row = p.rowvec ? p.rowvec + (orow / p.rowvec_div) * (long long)p.N : nullptr;
+        const __half* rv_row = p.rowvec ? p.rowvec + (orow / p.rowvec_div) * p.rowvec_ld : nullptr;
         const bool vec_ok = ((p.out_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                             (!p.residual || (((p.res_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
 #pragma unroll 1

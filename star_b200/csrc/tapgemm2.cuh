@@ -20,7 +20,30 @@
 #define STAR_GEMM_EXP 0
 #endif
 
+//   STAR_GEMM_TRACE 1: CTA 0 records clock64() timestamps of its producer / MMA / epilogue roles per tile into g_tg2_trace
+//                     (tools/gemm_trace.py reads it back through star_debug_read_trace); never set in the shipped library.
+#ifndef STAR_GEMM_TRACE
+#define STAR_GEMM_TRACE 0
+#endif
+
 namespace star {
+
+#if STAR_GEMM_TRACE
+__device__ long long g_tg2_trace[3][4096];        // [role][slot]: role 0 producer, 1 MMA, 2 epilogue (warp 4 lane 0)
+__device__ int g_tg2_trace_n[3];
+STAR_DEVINL void tg2_trace(int role, int event) {
+    if (blockIdx.x != 0) return;
+    const int i = g_tg2_trace_n[role];
+    if (i + 1 < 4096) {
+        g_tg2_trace[role][i] = event;
+        g_tg2_trace[role][i + 1] = clock64();
+        g_tg2_trace_n[role] = i + 2;
+    }
+}
+#define TG2_TRACE(role, event) tg2_trace(role, event)
+#else
+#define TG2_TRACE(role, event)
+#endif
 
 constexpr int TG2_THREADS = 384;      // warps 0-3: TMA, MMA, 2 idle; warps 4-11: epilogue (two warps per TMEM lane quadrant)
 constexpr int TG2_MAX_STAGES = 6;
@@ -144,6 +167,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
                 int org[4], n_tile;
                 tile_origin(tile, org, n_tile);
+                TG2_TRACE(0, 1);                                   // producer: tile start
                 for (int t = 0; t < p.ntaps; ++t) {
                     const int c1 = org[0] + p.tap[t][0], c2 = org[1] + p.tap[t][1];
                     const int c3 = org[2] + p.tap[t][2], c4 = org[3] + p.tap[t][3];
@@ -163,6 +187,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (++s == NS) { s = 0; ph ^= 1; }
                     }
                 }
+                TG2_TRACE(0, 2);                                   // producer: all operand loads of the tile issued
                 if (res_tma) {
                     // residual tile of THIS output tile, issued after its operand loads so that waiting for the
                     // previous epilogue to release the buffer never delays the operand prefetch
@@ -191,8 +216,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x, ++local) {
                 const int buf = local & 1;
+                TG2_TRACE(1, 1);                                   // MMA: waiting for the accumulator
                 mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
                 tc_fence_after();
+                TG2_TRACE(1, 2);                                   // MMA: accumulator free
                 const uint32_t acc = tmem_base + buf * ACC_STRIDE;
                 for (int i = 0; i < total_iters; ++i) {
                     mbar_wait(&full_bar[s], ph);
@@ -207,6 +234,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     if (++s == NS) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);
+                TG2_TRACE(1, 3);                                   // MMA: last instruction of the tile issued
             }
         }
     } else if (warp >= 4) {
@@ -242,11 +270,13 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     orow += (long long)g * mul;
                     mul *= p.on[i];
                 }
-                if (p.rowvec) rv_row = p.rowvec + (orow / p.rowvec_div) * (long long)p.N;
+                if (p.rowvec) rv_row = p.rowvec + (orow / p.rowvec_div) * p.rowvec_ld;
                 if (has_res && !res_tma) res_g = p.residual + orow * p.res_ld;
             }
+            if (leader) TG2_TRACE(2, 1);                           // epilogue: waiting for acc_full
             mbar_wait(&acc_full[buf], (local >> 1) & 1);
             tc_fence_after();
+            if (leader) TG2_TRACE(2, 2);                           // epilogue: accumulator complete
             if (res_tma) mbar_wait(res_full, local & 1);
             const uint32_t t_row = tmem_base + buf * ACC_STRIDE + lane_off;
             const int last_c0 = ((n_per_tile / 32 - 1 - ehalf) & ~1) * 32 + ehalf * 32;   // last chunk of this warp
@@ -259,10 +289,13 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ++pass_ctr;
             uint8_t* out_row = out_row0 + ob * SM::OUT_BYTES;
             if (leader) {
+                TG2_TRACE(2, 3);                                   // pass: before the staging-buffer wait
                 if (ex.dbuf) tma_store_wait_read_but_one();
                 else tma_store_wait_read();
+                TG2_TRACE(2, 4);                                   // pass: staging buffer free
             }
             epi_bar_sync();
+            if (leader) TG2_TRACE(2, 5);                           // pass: all epilogue warps past the first barrier
             const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
 #pragma unroll 1
             for (int c0 = pass0 + ehalf * 32; c0 < pass_end; c0 += 64) {
@@ -374,8 +407,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
             }
             if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
+            if (leader) TG2_TRACE(2, 6);                           // pass: this warp's chunks computed and staged
             fence_proxy_async_smem();
             epi_bar_sync();
+            if (leader) TG2_TRACE(2, 7);                           // pass: all warps staged
             if (leader && STAR_GEMM_EXP == 0) {
 #pragma unroll 1
                 for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {

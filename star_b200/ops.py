@@ -145,8 +145,9 @@ def conv2d_3x3(x, w9, bias=None, rowvec=None, rowvec_div=1, residual=None, out=N
         out = torch.empty((BT * H * W, Cout), dtype=_dt(), device=x.device)
     ldo = _rowmajor(out, "out")
     ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    ldrv = _rowmajor(rowvec, "rowvec") if rowvec is not None else 0           # a column slice of a wider matrix is fine
     L = _lib()
-    _L.check(L.star_conv2d_3x3(_p(x), _p(w9), _p(bias), _p(rowvec), int(rowvec_div), _p(residual), ldres,
+    _L.check(L.star_conv2d_3x3(_p(x), _p(w9), _p(bias), _p(rowvec), int(rowvec_div), ldrv, _p(residual), ldres,
                                _p(out), ldo, BT, H, W, Cin, Cout, _st()), "star_conv2d_3x3")
     return out
 

@@ -397,9 +397,7 @@ class ResBlock(nn.Module):
     def run(self, ctx, x, H, W):
         BT, HW = ctx.B * ctx.T, H * W
         lo, hi = self._temb_slice
-        temb = ctx.temb[:, lo:hi]
-        if not temb.is_contiguous():
-            temb = temb.contiguous()
+        temb = ctx.temb[:, lo:hi]                          # column slice of the one time-embedding GEMM: passed with its row pitch
         h = ops.groupnorm(x, *self._gn1, BT, 1e-5, True)
         h = ops.conv2d_3x3(h.view(BT, H, W, self.channels), *self._c1, rowvec=temb, rowvec_div=ctx.T * HW)
         h = ops.groupnorm(h, *self._gn2, BT, 1e-5, True)

@@ -92,6 +92,18 @@ def test_conv2d_3x3(env, BT, H, W, Cin, Cout, extras):
     assert_close(got, ref, what=f"conv3x3 {BT}x{H}x{W} {Cin}->{Cout} {extras}")
 
 
+def test_conv2d_rowvec_column_slice(env):
+    """the time-embedding operand is a column slice of the one [B, sum Cout] embedding GEMM (row pitch != Cout)"""
+    O, R = env
+    x = rnd(4, 10, 8, 320, seed=1)                                   # 2 clips x 2 frames
+    w9 = rnd(640, 3, 3, 320, seed=2, scale=(9 * 320) ** -0.5)
+    temb_all = rnd(2, 320 + 640 + 1280, seed=3)
+    rv = temb_all[:, 320:960]
+    assert not rv.is_contiguous()
+    got = O.conv2d_3x3(x, w9, None, rv, 2 * 80)
+    assert_close(got, R.conv2d_3x3(x, w9, None, rv, 2 * 80), what="conv3x3 + strided rowvec")
+
+
 @pytest.mark.parametrize("BT,H,W,C", [(2, 18, 16, 320), (3, 10, 8, 640), (1, 34, 32, 64), (2, 122, 216, 64)])
 def test_conv2d_s2(env, BT, H, W, C):
     O, R = env

@@ -16,6 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_nccl_sharded_pipeline(nproc):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
+    only = os.environ.get("STAR_MGPU_ONLY")                  # e.g. "8": run just that world size (GPU-minute budget)
+    if only and int(only) != nproc:
+        pytest.skip("STAR_MGPU_ONLY")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                         "--master-port", str(29500 + nproc), os.path.join(ROOT, "tools", "mgpu_check.py")], cwd=ROOT, capture_output=True,
                        text=True, timeout=900)
