@@ -631,7 +631,9 @@ def main():
                        "chunk_frames": chunk_frames, "unique_frames_per_s": unique_value,
                        "parallelism": f"chunk-parallel x{world}, per-step x0 all-gather" if world > 1 else "single GPU",
                        "l2": "activations (0.54 GB per tensor) exceed the 126 MB L2; no explicit flush",
-                       "step": "one solver step = 2 UNet+ControlNet forwards + guidance + solver update",
+                       "step": "one solver step = 2 UNet+ControlNet forwards (CFG) + guidance + solver update; the two forwards' common, "
+                               "text-independent prefix (stem, first temporal transformer, first ResBlock, first spatial self-attention "
+                               "of each network) is evaluated once -- bit-identical outputs (forward_cfg_pair), ~7 % of the step's FLOPs",
                        "vae": "timed separately (key `pipeline`); `value` and `e2e` are the latent-in / latent-out "
                               "denoise loop BASELINE.json's metric is quoted on"},
             "clocks": clk, "gpu_launches": int(launches),

@@ -84,12 +84,23 @@ class GaussianDiffusion(object):
             out = model(xt, t=t, **model_kwargs)
         else:
             assert isinstance(model_kwargs, list)
-            y_out = self._branch_out(xt, t, model, model_kwargs, 0, variant_info)
-            if guide_scale == 1.0:
-                out = y_out
+            pair = getattr(model, "forward_cfg_pair", None)
+            if guide_scale != 1.0 and pair is not None and set(model_kwargs[0]) == set(model_kwargs[1]) == {"y"}:
+                # the two branches differ only in the text embedding: the model evaluates their common, text-independent
+                # prefix once (bit-identical to two calls, tests/test_unet_gpu.py::test_cfg_pair_equals_two_forwards)
+                extra = {}
+                for kw in model_kwargs[2:]:
+                    extra.update(kw)
+                if len(model_kwargs) <= 3:
+                    extra["variant_info"] = variant_info
+                out = pair(xt, t, (model_kwargs[0]["y"], model_kwargs[1]["y"]), **extra)
             else:
-                u_out = self._branch_out(xt, t, model, model_kwargs, 1, variant_info)
-                out = (y_out, u_out)
+                y_out = self._branch_out(xt, t, model, model_kwargs, 0, variant_info)
+                if guide_scale == 1.0:
+                    out = y_out
+                else:
+                    u_out = self._branch_out(xt, t, model, model_kwargs, 1, variant_info)
+                    out = (y_out, u_out)
 
         if isinstance(out, tuple):
             x0 = self._guided_x0(out[0], out[1], xt, alphas, sigmas, guide_scale, guide_rescale, clamp, percentile)

@@ -189,6 +189,11 @@ class BasicTransformerBlock(nn.Module):
         return torch.cat([self.attn2.to_k.weight, self.attn2.to_v.weight], dim=0)
 
     def run_space(self, ctx, x, H, W, kv):
+        return self.run_space_back(ctx, *self.run_space_front(ctx, x, H, W), H, W, kv)
+
+    def run_space_front(self, ctx, x, H, W):
+        """Everything of the 'space' block that does not see the text: LIEM -> LN -> self-attention (+x) -> LN -> q of the text
+        cross-attention.  Identical for the two CFG branches of a solver step (same x, t, hint; only y differs)."""
         BT, C, heads = ctx.B * ctx.T, self.dim, self.n_heads
         HW = H * W
         gate = ops.liem_spatial_gate(x, self._liem, BT, H, W)
@@ -197,9 +202,12 @@ class BasicTransformerBlock(nn.Module):
         a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], BT, heads, HW, HW, 1, 0.125)
         x = ops.linear(a, self._o1_w, self._o1_b, residual=x)
         n = ops.layernorm(x, *self._ln[1])
-        q = ops.linear(n, self._q2)
+        return x, ops.linear(n, self._q2)
+
+    def run_space_back(self, ctx, x, q, H, W, kv):
+        BT, heads = ctx.B * ctx.T, self.n_heads
         k, v = kv
-        a = ops.attention(q, k, v, BT, heads, HW, ctx.context_rows, ctx.T, 0.125)
+        a = ops.attention(q, k, v, BT, heads, H * W, ctx.context_rows, ctx.T, 0.125)
         x = ops.linear(a, self._o2_w, self._o2_b, residual=x)
         n = ops.layernorm(x, *self._ln[2])
         return self.ff.run(n, x)
@@ -246,9 +254,16 @@ class SpatialTransformer(nn.Module):
         self.transformer_blocks[0]._pack()
 
     def run(self, ctx, x, H, W, kv):
+        return self.run_back(ctx, self.run_front(ctx, x, H, W), H, W, kv)
+
+    def run_front(self, ctx, x, H, W):
         h = ops.groupnorm(x, *self._gn, ctx.B * ctx.T, 1e-6, False)
         h = ops.linear(h, *self._in)
-        h = self.transformer_blocks[0].run_space(ctx, h, H, W, kv)
+        return (x,) + self.transformer_blocks[0].run_space_front(ctx, h, H, W)
+
+    def run_back(self, ctx, front, H, W, kv):
+        x, h, q = front
+        h = self.transformer_blocks[0].run_space_back(ctx, h, q, H, W, kv)
         return ops.linear(h, *self._out, residual=x)
 
 
@@ -509,18 +524,49 @@ class _UNetBase(nn.Module):
         self._packed = False
         return super()._load_from_state_dict(*a, **k)
 
-    def _begin(self, t, y, B, T):
-        """time embedding + text K/V for this network; returns ctx."""
+    def _begin_time(self, t, B, T):
+        """time embedding of every ResBlock of this network (one GEMM); returns ctx without the text part."""
         ctx = _Ctx(B, T)
         e = ops.sinusoidal(t, self.dim)
         w0, b0, w1, b1 = self._te
         e = ops.linear(e, w0, b0, flags=ops.FLAG_SILU_OUT)
         e = ops.linear(e, w1, b1, flags=ops.FLAG_SILU_OUT)         # = SiLU(time_embed(..)), input of every emb_layers
         ctx.temb = ops.linear(e, self._temb_w, self._temb_b)
-        y16 = y.to(HALF).reshape(-1, y.shape[-1]).contiguous()
-        ctx.context_rows = y.shape[1]
-        ctx.text_kv = ops.linear(y16, self._kv_w)
         return ctx
+
+    def _with_text(self, ctx, y):
+        """a copy of ctx carrying the text K/V of every spatial block for the embedding y (one GEMM)"""
+        c = _Ctx(ctx.B, ctx.T)
+        c.temb = ctx.temb
+        y16 = y.to(HALF).reshape(-1, y.shape[-1]).contiguous()
+        c.context_rows = y.shape[1]
+        c.text_kv = ops.linear(y16, self._kv_w)
+        return c
+
+    def _begin(self, t, y, B, T):
+        """time embedding + text K/V for this network; returns ctx."""
+        return self._with_text(self._begin_time(t, B, T), y)
+
+    # -- the part of the encoder that never sees the text ---------------------------------------------------------------------
+    # stem output -> temporal transformer of input_blocks[0] -> ResBlock and the front of the SpatialTransformer of
+    # input_blocks[1].  The two CFG branches of a solver step call the network with the same (x, t, hint) and different y
+    # (diffusion_sdedit.py:81,88), so this prefix -- incl. one finest-level self-attention -- is evaluated ONCE for both.
+    def _prefix_splittable(self):
+        b1 = self.input_blocks[1]
+        return (isinstance(b1, nn.ModuleList) and len(b1) == 3 and isinstance(b1[0], ResBlock)
+                and isinstance(b1[1], SpatialTransformer) and isinstance(b1[2], TemporalTransformer))
+
+    def _run_prefix(self, ctx, h, H, W):
+        """h = stem output.  Returns (h0, front): h0 = output of input_blocks[0], front = state of block 1 at the split point."""
+        h0 = self.input_blocks[0][1].run(ctx, h, H * W)
+        b1 = self.input_blocks[1]
+        r = b1[0].run(ctx, h0, H, W)
+        return h0, b1[1].run_front(ctx, r, H, W)
+
+    def _finish_block1(self, ctx, front, H, W):
+        b1 = self.input_blocks[1]
+        h = b1[1].run_back(ctx, front, H, W, self._kv(ctx, b1[1]))
+        return b1[2].run(ctx, h, H * W)
 
     def _kv(self, ctx, m):
         a, b, c = self._kv_slices[id(m)]
@@ -607,35 +653,66 @@ class ControlledV2VUNet(Vid2VidSDUNet):
         like the reference's ``.half()`` model under autocast (ref :1717-1809)."""
         if hint_chunk is not None:
             hint = hint_chunk                                              # ref :1743-1744
+        return self._forward_branches(x, t, (y,), hint)[0]
+
+    @torch.no_grad()
+    def forward_cfg_pair(self, x, t, y_pair, hint=None, hint_chunk=None, variant_info=None):
+        """Both classifier-free-guidance branches of one solver step: ``(forward(x, t, y_pair[0], hint), forward(x, t, y_pair[1],
+        hint))`` bit for bit, with the text-independent prefix of both networks (stem, first temporal transformer, first ResBlock,
+        and the first spatial block up to the query of its text cross-attention -- one finest-level self-attention per network)
+        evaluated once.  The reference makes two full calls (diffusion_sdedit.py:81,88)."""
+        if hint_chunk is not None:
+            hint = hint_chunk
+        return tuple(self._forward_branches(x, t, tuple(y_pair), hint))
+
+    def _forward_branches(self, x, t, ys, hint):
         if hint is None:
             raise ValueError("ControlledV2VUNet needs the LR latent (hint / hint_chunk)")
         self._ensure_packed()
-        B, _, T, H, W = x.shape
-        if H % 8 != 2 or W % 8 != 0:
-            raise ValueError(f"latent {H}x{W}: H must be 2 (mod 8) and W 0 (mod 8) for the UNet's "
+        B, _, T, H0, W0 = x.shape
+        if H0 % 8 != 2 or W0 % 8 != 0:
+            raise ValueError(f"latent {H0}x{W0}: H must be 2 (mod 8) and W 0 (mod 8) for the UNet's "
                              "down/up-sampling to close (ref :709, :564)")
         t = t.to(x.device)
         xt = ops.nchw5_to_tokens(x)
         ht = ops.nchw5_to_tokens(hint)
-        control = self.VideoControlNet.run(xt, ht, t, y, B, T, H, W)      # ref :1746
-        ctx = self._begin(t, y, B, T)
         BT = B * T
-        h = ops.conv2d_3x3_c4(xt.view(BT, H, W, self.in_dim), *self._stem)
-        h = self.input_blocks[0][1].run(ctx, h, H * W)
-        xs = [(h, H, W)]
-        for block in list(self.input_blocks)[1:]:
-            h, H, W = self._run_block(ctx, block, h, H, W)
-            xs.append((h, H, W))
-        h, H, W = self._run_block(ctx, self.middle_block, h, H, W)
-        h = ops.add(control.pop(), h)                                      # ref :1784-1785
-        for block in self.output_blocks:
-            skip, _, _ = xs.pop()
-            h = ops.concat_add(h, skip, control.pop())                     # ref :1792
-            h, H, W = self._run_block(ctx, block, h, H, W)
-        gw, gb, w9, b9 = self._head
-        h = ops.groupnorm(h, gw, gb, BT, 1e-5, True)
-        h = ops.conv2d_3x3(h.view(BT, H, W, h.shape[1]), w9, b9)          # ref :1805
-        return ops.tokens_to_nchw5(h, B, self.out_dim, T, H, W)           # ref :1808
+        cn = self.VideoControlNet
+        share = len(ys) > 1 and self._prefix_splittable() and cn._prefix_splittable()
+        base = self._begin_time(t, B, T)
+        cn_shared = cn.run_shared(xt, ht, t, B, T, H0, W0) if share else None
+        if share:
+            h = ops.conv2d_3x3_c4(xt.view(BT, H0, W0, self.in_dim), *self._stem)
+            h0, front = self._run_prefix(base, h, H0, W0)
+        outs = []
+        for y in ys:
+            H, W = H0, W0
+            control = cn.run_text(cn_shared, y, H, W) if share else cn.run(xt, ht, t, y, B, T, H, W)      # ref :1746
+            ctx = self._with_text(base, y)
+            if share:
+                xs = [(h0, H, W)]
+                h = self._finish_block1(ctx, front, H, W)
+                xs.append((h, H, W))
+                rest = list(self.input_blocks)[2:]
+            else:
+                h = ops.conv2d_3x3_c4(xt.view(BT, H, W, self.in_dim), *self._stem)
+                h = self.input_blocks[0][1].run(ctx, h, H * W)
+                xs = [(h, H, W)]
+                rest = list(self.input_blocks)[1:]
+            for block in rest:
+                h, H, W = self._run_block(ctx, block, h, H, W)
+                xs.append((h, H, W))
+            h, H, W = self._run_block(ctx, self.middle_block, h, H, W)
+            h = ops.add(control.pop(), h)                                      # ref :1784-1785
+            for block in self.output_blocks:
+                skip, _, _ = xs.pop()
+                h = ops.concat_add(h, skip, control.pop())                     # ref :1792
+                h, H, W = self._run_block(ctx, block, h, H, W)
+            gw, gb, w9, b9 = self._head
+            h = ops.groupnorm(h, gw, gb, BT, 1e-5, True)
+            h = ops.conv2d_3x3(h.view(BT, H, W, h.shape[1]), w9, b9)          # ref :1805
+            outs.append(ops.tokens_to_nchw5(h, B, self.out_dim, T, H, W))     # ref :1808
+        return outs
 
 
 class VideoControlNet(_UNetBase):
@@ -678,9 +755,28 @@ class VideoControlNet(_UNetBase):
         h = ops.conv2d_3x3_c4(xt.view(BT, H, W, self.in_dim), *self._stem, residual=hint)  # ref :2189-2194
         h = self.input_blocks[0][1].run(ctx, h, H * W)
         outs = [ops.linear(h, *self._zc[0])]
-        for k, block in enumerate(list(self.input_blocks)[1:], start=1):
+        return self._run_rest(ctx, h, outs, 1, H, W)
+
+    def _run_rest(self, ctx, h, outs, first, H, W):
+        for k, block in enumerate(list(self.input_blocks)[first:], start=first):
             h, H, W = self._run_block(ctx, block, h, H, W)
             outs.append(ops.linear(h, *self._zc[k]))
         h, H, W = self._run_block(ctx, self.middle_block, h, H, W)
         outs.append(ops.linear(h, *self._mid_out))
         return outs
+
+    def run_shared(self, xt, ht, t, B, T, H, W):
+        """The text-independent prefix of run() (see _UNetBase._run_prefix): evaluated once per solver step for both CFG branches."""
+        self._ensure_packed()
+        base = self._begin_time(t, B, T)
+        BT = B * T
+        hint = ops.conv2d_3x3_c4(ht.view(BT, H, W, 4), *self._hint)
+        h = ops.conv2d_3x3_c4(xt.view(BT, H, W, self.in_dim), *self._stem, residual=hint)
+        h0, front = self._run_prefix(base, h, H, W)
+        return base, ops.linear(h0, *self._zc[0]), front
+
+    def run_text(self, shared, y, H, W):
+        base, out0, front = shared
+        ctx = self._with_text(base, y)
+        h = self._finish_block1(ctx, front, H, W)
+        return self._run_rest(ctx, h, [out0, ops.linear(h, *self._zc[1])], 2, H, W)

@@ -98,6 +98,38 @@ def test_unet_host_graph_on_emulated_kernels(small_sd, monkeypatch):
         assert err < 1.5 * c["ref_fp16_rel_err"] and err < 4e-3, (err, c["ref_fp16_rel_err"])
 
 
+def test_cfg_pair_forward_equals_two_forwards_on_emulated_kernels(small_sd, monkeypatch):
+    """forward_cfg_pair (shared text-independent prefix) == two forward() calls, bit for bit (host graph on the emulated kernels);
+    the sampler's denoise() takes the pair path and reproduces the two-call result exactly."""
+    from oracle import kernel_ref as KR
+    from star_b200 import ops
+    from star_b200.video_to_video.diffusion.diffusion_sdedit import GaussianDiffusion
+    from star_b200.video_to_video.diffusion.schedules_sdedit import noise_schedule
+    from star_b200.video_to_video.modules.unet_v2v import ControlledV2VUNet
+    for name in dir(KR):
+        if not name.startswith("_") and callable(getattr(KR, name)) and hasattr(ops, name):
+            monkeypatch.setattr(ops, name, getattr(KR, name))
+    with torch.device("meta"):
+        net = ControlledV2VUNet(**SMALL_KW)
+    net.load_state_dict(small_sd, assign=True)
+    net = net.half().eval()
+    x, hint, y = make_inputs(0, 1, 3, 10, 8)
+    _, _, ny = make_inputs(1, 1, 3, 10, 8)
+    t = torch.tensor([500])
+    a, b = net(x, t, y, hint=hint), net(x, t, ny, hint=hint)
+    pa, pb = net.forward_cfg_pair(x, t, (y, ny), hint=hint)
+    assert torch.equal(a, pa) and torch.equal(b, pb) and not torch.equal(a, b)
+    d = GaussianDiffusion(noise_schedule(schedule="logsnr_cosine_interp", n=1000, zero_terminal_snr=True, scale_min=2.0, scale_max=4.0))
+    kw = [{"y": y}, {"y": ny}, {"hint": hint}]
+    x0_pair = d.denoise(x, t, None, net, kw, guide_scale=7.5, guide_rescale=0.2)[-2]
+
+    class TwoCalls(torch.nn.Module):                    # hides forward_cfg_pair: the reference's two-call structure
+        def forward(self, *a, **k):
+            return net(*a, **k)
+    x0_two = d.denoise(x, t, None, TwoCalls(), kw, guide_scale=7.5, guide_rescale=0.2)[-2]
+    assert torch.equal(x0_pair, x0_two)
+
+
 def test_product_has_no_cpu_fallback():
     from star_b200 import lib, ops
     x = torch.zeros(8, 64, dtype=torch.float16)

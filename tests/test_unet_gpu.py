@@ -46,6 +46,22 @@ def test_unet_deterministic(small_net):
     assert torch.equal(a, b)
 
 
+def test_cfg_pair_equals_two_forwards(small_net):
+    """the CFG branches' shared prefix evaluated once: bit-identical to two full forwards on the real kernels"""
+    x, hint, y = make_inputs(9, 1, 4, 18, 16)
+    _, _, ny = make_inputs(10, 1, 4, 18, 16)
+    t = torch.tensor([500]).cuda()
+    from star_b200 import ops
+    n0 = ops.launch_count()
+    a, b = small_net(x.cuda(), t, y.cuda(), hint=hint.cuda()), small_net(x.cuda(), t, ny.cuda(), hint=hint.cuda())
+    n1 = ops.launch_count()
+    pa, pb = small_net.forward_cfg_pair(x.cuda(), t, (y.cuda(), ny.cuda()), hint=hint.cuda())
+    n2 = ops.launch_count()
+    assert torch.equal(a, pa) and torch.equal(b, pb) and not torch.equal(a, b)
+    print(f"kernel launches: two forwards {n1 - n0}, CFG pair {n2 - n1}")
+    assert n2 - n1 < n1 - n0
+
+
 def test_sampler_with_unet_chunked(small_net):
     """sample_sr over 2 overlapping chunks, 2 steps, CFG 7.5, identical noise: product on GPU vs the
     real reference (fp32, CPU)."""
