@@ -227,13 +227,10 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     if (make_tmap(&to, d.out, 5, odim, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     // Output staging depth.  Short reductions are epilogue-bound (the main loop alone runs at 75-82 % of peak, the serialised
     // store drain costs 25-30 %: profiles/r02_kbench_gemm_attribution.log) -> two staging buffers, one operand stage fewer.
-    ex.dbuf = (BN == 256 && (long long)d.ntaps * d.K <= STAR_GEMM_DBUF_MAXK) ? 1 : 0;
+    ex.dbuf = ((long long)d.ntaps * d.K <= STAR_GEMM_DBUF_MAXK) ? 1 : 0;
     ex.res_direct = 0;
-    bool res_tma = d.residual && TapGemm2Smem<BN>::RES_TMA;
-    if (ex.dbuf && res_tma && TapGemm2Smem<BN>::stages(true, true) < 3) {          // BN = 160: no room for both -> direct residual loads
-        ex.res_direct = 1;
-        res_tma = false;
-    }
+    const bool res_tma = d.residual && TapGemm2Smem<BN>::RES_TMA;
+    if (ex.dbuf && TapGemm2Smem<BN>::stages(res_tma, true) < 3) ex.dbuf = 0;       // BN = 160 + residual: no room for a second buffer
     if (res_tma) {
         strides(d.ldres, rstr);
         if (make_tmap(&tr, d.residual, 5, odim, rstr, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -242,7 +239,25 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     }
     const int grid = (int)std::min<long long>(total, num_sms());
     ex.stages = TapGemm2Smem<BN>::stages(res_tma, ex.dbuf != 0);
-    tapgemm2_kernel<BN><<<grid, TG2_THREADS, TapGemm2Smem<BN>::total(res_tma, ex.dbuf != 0), st>>>(ta, tw, to, tr, p, ex);
+    const size_t smem = TapGemm2Smem<BN>::total(res_tma, ex.dbuf != 0);
+    // compile-time specialised epilogues for the three shapes that carry ~all of the linear / conv time
+    const bool extras = d.rowvec || d.colscale || (d.flags & (TG_GELU_TANH | TG_SILU_OUT));
+    bool launched = false;
+    if (geglu && !d.residual && !extras) {
+        if constexpr (BN != 160) {
+            tapgemm2_kernel<BN, TG2_EPI_GEGLU><<<grid, TG2_THREADS, smem, st>>>(ta, tw, to, tr, p, ex);
+            launched = true;
+        }
+    } else if (!geglu && !d.residual && !extras) {
+        tapgemm2_kernel<BN, TG2_EPI_PLAIN><<<grid, TG2_THREADS, smem, st>>>(ta, tw, to, tr, p, ex);
+        launched = true;
+    } else if (!geglu && res_tma && !extras) {
+        if constexpr (TapGemm2Smem<BN>::RES_TMA) {
+            tapgemm2_kernel<BN, TG2_EPI_RES><<<grid, TG2_THREADS, smem, st>>>(ta, tw, to, tr, p, ex);
+            launched = true;
+        }
+    }
+    if (!launched) tapgemm2_kernel<BN, TG2_EPI_GENERIC><<<grid, TG2_THREADS, smem, st>>>(ta, tw, to, tr, p, ex);
     STAR_LAUNCH_CHECK("tapgemm2");
     return 0;
 }
@@ -314,9 +329,16 @@ static int star_init_on_current(int device) {
 #define STAR_SMEM_ATTR(kernel, bytes) STAR_CUDA((cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))))
     STAR_SMEM_ATTR(tapgemm_kernel<128>, TapGemmSmem<128>::TOTAL);
     STAR_SMEM_ATTR(tapgemm_kernel<160>, TapGemmSmem<160>::TOTAL);
-    STAR_SMEM_ATTR(tapgemm2_kernel<128>, 232448);
-    STAR_SMEM_ATTR(tapgemm2_kernel<160>, 232448);
-    STAR_SMEM_ATTR(tapgemm2_kernel<256>, 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<128, TG2_EPI_GENERIC>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<160, TG2_EPI_GENERIC>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<256, TG2_EPI_GENERIC>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<128, TG2_EPI_PLAIN>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<160, TG2_EPI_PLAIN>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<256, TG2_EPI_PLAIN>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<128, TG2_EPI_RES>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<160, TG2_EPI_RES>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<128, TG2_EPI_GEGLU>), 232448);
+    STAR_SMEM_ATTR((tapgemm2_kernel<256, TG2_EPI_GEGLU>), 232448);
     STAR_SMEM_ATTR(attn_fwd_kernel<false>, AttnSmemT<false>::TOTAL);
     STAR_SMEM_ATTR(attn_fwd_kernel<true>, AttnSmemT<true>::TOTAL);
     STAR_SMEM_ATTR(attn4_fwd_kernel, Attn4Smem::TOTAL);

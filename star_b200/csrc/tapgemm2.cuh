@@ -6,8 +6,12 @@
 //     results are staged in swizzled shared memory and leave through TMA stores (hardware clips ragged
 //     tile edges and the N tail), bias / time-embedding rows are read with 128-bit loads
 // Tile widths BN = 128 / 160 / 256 (star_abi.cu picks: 256 wherever the padded width wastes little; 6 / 5 / 4 operand
-// stages).  Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle,
-// warps 4-11 epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and every other 32-column chunk
+// stages).  Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warp 2 idle, warp 3 TMA-STORE thread
+// (round 2: the role timeline of one CTA, profiles/r02_gemm_trace_qkv_before.log, showed the epilogue as the bottleneck of the
+// short-K GEMMs -- 7 750 clk per 128x256 tile against 3 500 for loads + MMA -- with ~970 clk per pass spent by the epilogue
+// leader ISSUING the four 5-D TMA stores while the other 255 epilogue threads waited at a barrier, and three bar.sync per
+// pass; now the epilogue warps only compute and stage, hand a full staging buffer to the store thread through an mbarrier
+// and continue with the other buffer), warps 4-11 epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and every other 32-column chunk
 // (the GEGLU / residual epilogues are instruction-bound with one warp per quadrant).
 #pragma once
 #include "common.cuh"
@@ -90,7 +94,13 @@ struct TapGemm2Extra {
     int res_direct;       // 1: read the residual with direct 16-byte loads even where this BN would prefetch it by TMA
 };
 
-template <int BN>
+// EPI selects a compile-time specialisation of the epilogue (the role timeline showed the generic epilogue -- ~1 500 SASS
+// instructions of run-time-flag paths per 32-column chunk -- as the limiter of the short-K GEMMs):
+//   0 generic (every flag / pointer combination)      1 plain: (+bias) only
+//   2 (+bias) + TMA-prefetched residual                3 GEGLU (+bias)
+enum { TG2_EPI_GENERIC = 0, TG2_EPI_PLAIN = 1, TG2_EPI_RES = 2, TG2_EPI_GEGLU = 3 };
+
+template <int BN, int EPI = TG2_EPI_GENERIC>
 __global__ void __launch_bounds__(TG2_THREADS, 1)
 tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -103,7 +113,9 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int NS = ex.stages;
     const int OFF_OUT = NS * SM::STAGE_BYTES;
     const int OFF_RES = OFF_OUT + SM::OUT_BYTES * (ex.dbuf ? 2 : 1);
-    const bool res_tma = SM::RES_TMA && p.residual != nullptr && !ex.res_direct;   // residual tile prefetched by TMA (else: direct loads)
+    constexpr bool GEN = EPI == TG2_EPI_GENERIC;
+    // residual tile prefetched by TMA (else: direct loads)
+    const bool res_tma = EPI == TG2_EPI_RES ? true : (GEN && SM::RES_TMA && p.residual != nullptr && !ex.res_direct);
     const int OFF_BAR = OFF_RES + (res_tma ? SM::OUT_BYTES : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + TG2_MAX_STAGES;
@@ -111,12 +123,18 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* acc_empty = acc_full + 2;              // 2
     uint64_t* res_full = acc_empty + 2;              // 1
     uint64_t* res_empty = res_full + 1;              // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+    uint64_t* stage_full = res_empty + 1;            // 2   epilogue warps -> store thread: staging buffer b holds a finished pass
+    uint64_t* stage_empty = stage_full + 2;          // 2   store thread -> epilogue warps: the TMA stores of buffer b have read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const bool geglu = (p.flags & TG_GEGLU) != 0;
-    const bool has_res = p.residual != nullptr;
+    const bool geglu = EPI == TG2_EPI_GEGLU ? true : (GEN && (p.flags & TG_GEGLU) != 0);
+    const bool has_res = EPI == TG2_EPI_RES ? true : (GEN && p.residual != nullptr);
+    const bool has_rowvec = GEN && p.rowvec != nullptr;
+    const bool has_colscale = GEN && p.colscale != nullptr;
+    const bool act_tanh = GEN && (p.flags & TG_GELU_TANH) != 0;
+    const bool act_silu = GEN && (p.flags & TG_SILU_OUT) != 0;
     const int n_per_tile = geglu ? BN / 2 : BN;
     const int total_iters = p.ntaps * p.k_chunks;
 
@@ -138,6 +156,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             mbar_init(res_full, 1);
             mbar_init(res_empty, 256);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&stage_full[b], 256);
+                mbar_init(&stage_empty[b], 1);
+            }
             fence_barrier_init();
         }
         __syncwarp();
@@ -237,6 +259,33 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 TG2_TRACE(1, 3);                                   // MMA: last instruction of the tile issued
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------ TMA-store thread: drains finished staging buffers
+        if (lane == 0) {
+            constexpr int PASS_COLS = SM::OUT_COLS;
+            int pc = 0;                                    // passes so far (same sequence as the epilogue warps)
+            for (int tile = blockIdx.x; tile < ex.num_tiles; tile += gridDim.x) {
+                int org[4], n_tile;
+                tile_origin(tile, org, n_tile);
+                const int n_base = n_tile * n_per_tile;
+                for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS, ++pc) {
+                    const int ob = ex.dbuf ? (pc & 1) : 0;
+                    const int use = ex.dbuf ? (pc >> 1) : pc;          // how often this buffer has been used before
+                    const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
+                    mbar_wait(&stage_full[ob], use & 1);
+#pragma unroll 1
+                    for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
+                        if (STAR_GEMM_EXP == 0 && n_base + pass0 + sb * 32 < p.N)
+                            tma_store_5d(&tmap_out, smem + OFF_OUT + ob * SM::OUT_BYTES + sb * 8192, n_base + pass0 + sb * 32,
+                                         org[0], org[1], org[2], org[3]);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();                 // with two buffers the epilogue warps fill the other one meanwhile
+                    mbar_arrive(&stage_empty[ob]);
+                }
+            }
+            tma_store_wait_all();
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue warps 4..11
         const int q = warp & 3;
@@ -258,7 +307,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // (unet_v2v.py:684; rows of one tile may belong to different clips) and direct residual loads
             const __half* rv_row = nullptr;
             const __half* res_g = nullptr;
-            if (p.rowvec || (has_res && !res_tma)) {
+            if (has_rowvec || (has_res && !res_tma)) {
                 int rr = r;
                 long long orow = 0, mul = 1;
 #pragma unroll
@@ -270,7 +319,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     orow += (long long)g * mul;
                     mul *= p.on[i];
                 }
-                if (p.rowvec) rv_row = p.rowvec + (orow / p.rowvec_div) * p.rowvec_ld;
+                if (has_rowvec) rv_row = p.rowvec + (orow / p.rowvec_div) * p.rowvec_ld;
                 if (has_res && !res_tma) res_g = p.residual + orow * p.res_ld;
             }
             if (leader) TG2_TRACE(2, 1);                           // epilogue: waiting for acc_full
@@ -283,19 +332,14 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             constexpr int PASS_COLS = SM::OUT_COLS;
 #pragma unroll 1
             for (int pass0 = 0; pass0 < n_per_tile; pass0 += PASS_COLS) {
-            // the TMA stores that last used this staging buffer must have finished reading it: the previous pass with one
-            // buffer, the pass before the previous one with two
+            // the TMA stores that last used this staging buffer must have finished reading it (store thread -> stage_empty)
             const int ob = ex.dbuf ? (pass_ctr & 1) : 0;
+            const int use = ex.dbuf ? (pass_ctr >> 1) : pass_ctr;
             ++pass_ctr;
             uint8_t* out_row = out_row0 + ob * SM::OUT_BYTES;
-            if (leader) {
-                TG2_TRACE(2, 3);                                   // pass: before the staging-buffer wait
-                if (ex.dbuf) tma_store_wait_read_but_one();
-                else tma_store_wait_read();
-                TG2_TRACE(2, 4);                                   // pass: staging buffer free
-            }
-            epi_bar_sync();
-            if (leader) TG2_TRACE(2, 5);                           // pass: all epilogue warps past the first barrier
+            if (leader) TG2_TRACE(2, 3);                           // pass: before the staging-buffer wait
+            mbar_wait(&stage_empty[ob], (use & 1) ^ 1);
+            if (leader) TG2_TRACE(2, 4);                           // pass: staging buffer free
             const int pass_end = (pass0 + PASS_COLS < n_per_tile) ? pass0 + PASS_COLS : n_per_tile;
 #pragma unroll 1
             for (int c0 = pass0 + ehalf * 32; c0 < pass_end; c0 += 64) {
@@ -346,11 +390,11 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }
-                if (p.flags & TG_GELU_TANH) {
+                if (act_tanh) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_f(f[j]);
                 }
-                if (p.colscale) {
+                if (has_colscale) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (n0 + u * 8 + 8 <= p.N) {
@@ -361,7 +405,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                     }
                 }
-                if (rv_row) {
+                if (has_rowvec && rv_row) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (n0 + u * 8 + 8 <= p.N) {
@@ -381,7 +425,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[u * 8 + e] += rv[e];
                     }
-                } else if (res_g) {
+                } else if (GEN && res_g) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (n0 + u * 8 + 8 <= p.N) {
@@ -392,7 +436,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                     }
                 }
-                if (p.flags & TG_SILU_OUT) {
+                if (act_silu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
                 }
@@ -408,20 +452,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             if (res_tma && pass_end == n_per_tile) mbar_arrive(res_empty);
             if (leader) TG2_TRACE(2, 6);                           // pass: this warp's chunks computed and staged
-            fence_proxy_async_smem();
-            epi_bar_sync();
-            if (leader) TG2_TRACE(2, 7);                           // pass: all warps staged
-            if (leader && STAR_GEMM_EXP == 0) {
-#pragma unroll 1
-                for (int sb = 0; sb < (pass_end - pass0) / 32; ++sb) {
-                    if (n_base + pass0 + sb * 32 < p.N)
-                        tma_store_5d(&tmap_out, smem + OFF_OUT + ob * SM::OUT_BYTES + sb * 8192, n_base + pass0 + sb * 32, org[0], org[1], org[2], org[3]);
-                }
-                tma_store_commit();
-            }
+            fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA store (async proxy)
+            mbar_arrive(&stage_full[ob]);
             }
         }
-        if (leader) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 1) {
