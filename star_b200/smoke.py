@@ -32,3 +32,9 @@ def run_smoke():
     print(f"smoke: ControlledV2VUNet forward on cuda:0, {launches} star kernels, rel-L2 vs fp32 oracle = {err:.3e}")
     if not (err < 4e-3) or launches == 0:
         raise RuntimeError(f"smoke failed: rel-L2 {err:.3e}, launches {launches}")
+    # the solver step's CFG pair (shared text-independent prefix) must reproduce the single forwards bit for bit
+    pa, pb = net.forward_cfg_pair(x.cuda(), t.cuda(), (y.cuda(), -y.cuda()), hint=hint.cuda())
+    other = net(x.cuda(), t.cuda(), -y.cuda(), hint=hint.cuda())
+    torch.cuda.synchronize()
+    if not (torch.equal(pa, out) and torch.equal(pb, other)):
+        raise RuntimeError("smoke failed: forward_cfg_pair differs from two forwards")

@@ -183,7 +183,11 @@ class GaussianDiffusion(object):
                 and dist.is_available() and dist.is_initialized():
             world, rank = dist.get_world_size(), dist.get_rank()
         mode = "exact" if chunk_parallel == "auto" else chunk_parallel
-        if world > 1 and solver == 'dpmpp_2m_sde' and kwargs.get('noise_sampler') is None:
+        # Ranks of one job must integrate the same SDE path -- also for single-chunk clips, where every rank evaluates the whole
+        # clip and the pipeline then shards only the VAE legs: share rank 0's noise seed whenever a process group exists.
+        group = (chunk_parallel in ("auto", "exact", "literal") and dist.is_available() and dist.is_initialized()
+                 and dist.get_world_size() > 1)
+        if group and solver == 'dpmpp_2m_sde' and kwargs.get('noise_sampler') is None:
             # every rank applies the same solver update: share the SDE noise stream (rank 0's seed)
             from .solvers_sdedit import IntervalNoiseSampler
             sd = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(noise.device)

@@ -89,8 +89,9 @@ def main():
         M._dist_info = real
     # the posterior sample of each frame is drawn by the rank that encodes it: compare through a tolerance on the pixels
     err = ((out_sharded - out_single).norm() / out_single.norm()).item()
-    gathered = [torch.empty_like(out_sharded, device=dev) for _ in range(world)]
-    dist.all_gather(gathered, out_sharded.to(dev))
+    mine = out_sharded.to(dev).contiguous()
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
     identical = all(torch.equal(gathered[0], t) for t in gathered)
     print(f"[rank {rank}] test() sharded: every rank returns the identical video: {identical}; vs un-sharded run (different posterior-"
           f"sample RNG streams): rel-L2 {err:.3e}", flush=True)
