@@ -118,9 +118,9 @@ def measured_peaks():
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_attn4_split.txt")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_attn4.txt")
     if not os.path.isfile(path):
-        path = os.path.join(ROOT, "profiles", "r01_ncu_attn4.txt")
+        path = os.path.join(ROOT, "profiles", "r01_ncu_attn4_split.txt")
     if not os.path.isfile(path):
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -572,12 +572,12 @@ def main():
         flops = 4.0 * hw0 * hw0 * 64 * batch * heads
         avg = sum(t for _, t in attn_ms) / len(attn_ms)
         ach = flops / (avg * 1e-3) / 1e12
-        roof = {"kernel": "attn4_fwd_kernel<0,1> (spatial self-attention, finest level, row-split softmax)", "bound": "tensor",
+        roof = {"kernel": "attn4_fwd_kernel (spatial self-attention, finest level, row-split softmax)", "bound": "tensor",
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "peak_source": peaks["source"], "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg,
                 "launches_timed": len(attn_ms), "traffic": ncu_traffic_bytes(),
                 "traffic_source": "dram__bytes_read+write of one `ncu --set full` capture of this kernel at this shape "
-                                  "(profiles/r01_ncu_attn4_split.txt); a constant of the kernel, not re-measured per run",
+                                  "(profiles/r02_ncu_attn4.txt); a constant of the kernel, not re-measured per run",
                 "algorithmic_bytes_per_launch": 4.0 * batch * heads * hw0 * 64 * 2,
                 "share_of_step": sum(t for _, t in attn_ms) / sum(per_op.values())}
     if args.trace_out and rank == 0:

@@ -273,15 +273,21 @@ class AutoencoderKLTemporalDecoder(nn.Module):
         q = ops.linear(xn, a["q"][0], a["q"][1])
         k = ops.linear(xn, a["k"][0], a["k"][1])
         ld = (HW + 7) // 8 * 8
-        S = torch.empty((HW, ld), dtype=HALF, device=x.device)
+        # logits are materialised for a block of query rows at a time (<= 0.6 GB at any resolution the softmax kernel accepts:
+        # 102 400 key columns = a 2 560 x 2 560-pixel frame); columns HW..ld of S are zeroed by star_softmax_rows
+        rb = max(128, min(HW, (1 << 28) // ld // 128 * 128))
+        S = torch.empty((min(rb, HW), ld), dtype=HALF, device=x.device)
         vt = torch.zeros((C, ld), dtype=HALF, device=x.device)
         o = torch.empty_like(x)
         for f in range(n):
             rows = slice(f * HW, (f + 1) * HW)
             ops.linear(a["v"], xn[rows], out=vt[:, :HW])                    # V^T = W_v X^T  [C, HW]
-            ops.linear(q[rows], k[rows], out=S[:, :HW])                     # logits, 1/sqrt(C) already in W_q
-            ops.softmax_rows(S, HW)
-            ops.linear(S, vt, out=o[rows])                                  # P V
+            for r0 in range(0, HW, rb):
+                r1 = min(HW, r0 + rb)
+                Sb = S[: r1 - r0]
+                ops.linear(q[f * HW + r0:f * HW + r1], k[rows], out=Sb[:, :HW])   # logits, 1/sqrt(C) already in W_q
+                ops.softmax_rows(Sb, HW)
+                ops.linear(Sb, vt, out=o[f * HW + r0:f * HW + r1])          # P V
         return ops.linear(o, a["o"][0], a["o"][1], residual=x)
 
     # ---- public surface ----------------------------------------------------------------------------------
