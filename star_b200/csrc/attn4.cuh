@@ -31,6 +31,10 @@
 #ifndef STAR_ATTN_POLY
 #define STAR_ATTN_POLY 0
 #endif
+//   STAR_ATTN_TRACE 1   : CTA (0,0,0) records clock64() of the softmax phases of both tiles per KV step (tools/attn_trace.py).
+#ifndef STAR_ATTN_TRACE
+#define STAR_ATTN_TRACE 0
+#endif
 
 namespace star {
 
@@ -41,6 +45,24 @@ STAR_DEVINL float a4_ld_shared_f32(uint32_t addr) {
     return v;
 }
 STAR_DEVINL void a4_named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+#if STAR_ATTN_TRACE
+__device__ long long g_a4_trace[2][8192];          // [query tile][slot]: (event, clock) pairs of warp 4 / warp 12 lane 0
+__device__ int g_a4_trace_n[2];
+STAR_DEVINL void a4_trace(int t, int event, int& i) {      // the slot counter lives in a register: an event costs ~2 stores
+    if (i + 1 < 8192) {
+        long long c;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");
+        g_a4_trace[t][i] = event;
+        g_a4_trace[t][i + 1] = c;
+        i += 2;
+        g_a4_trace_n[t] = i;
+    }
+}
+#define A4_TRACE(ev) do { if (trace_me) a4_trace(t, ev, trace_i); } while (0)
+#else
+#define A4_TRACE(ev)
+#endif
 
 struct TagFalse { static constexpr bool value = false; };
 struct TagTrue { static constexpr bool value = true; };
@@ -229,18 +251,24 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int bar_id = 1 + t;
             const float sl2 = p.scale_log2;
             float m_used = 0.f, l_run = 0.f;
-
+#if STAR_ATTN_TRACE
+            const bool trace_me = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && half == 0 && quad == 0 && lane == 0;
+            int trace_i = 0;
+#endif
             auto kv_tile = [&](const int j, auto tail_tag) {
                 constexpr bool tail = decltype(tail_tag)::value;
                 const int kbase = j * 128 + half * 64;
+                A4_TRACE(1);
                 mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
+                A4_TRACE(2);
                 uint32_t v[64];
                 tmem_ld32(t_s, v);
                 tmem_ld32(t_s + 32, v + 32);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&s_free[t]);
+                A4_TRACE(3);
                 if (tail) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i)
@@ -259,6 +287,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 a4_st_shared_f32(x_slot + (uint32_t)half * 512u + (uint32_t)r * 4u, mx_mine);
                 a4_named_bar_sync(bar_id, 256);
                 const float mx = fmaxf(mx_mine, a4_ld_shared_f32(x_slot + (uint32_t)(half ^ 1) * 512u + (uint32_t)r * 4u));
+                A4_TRACE(4);
                 const float mc = mx * sl2;
                 float factor = 1.f;
                 bool need = false;
@@ -295,9 +324,11 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (pingpong) mbar_arrive(&turn[1 - t]);
                 float l_lo, l_hi;
                 f2_unpack(f2_add(l0, l1), l_lo, l_hi);
+                A4_TRACE(5);
                 if (j > 0) {
                     mbar_wait(&pv_done[t], (j - 1) & 1);         // P buffer free, O_t stable
                     tc_fence_after();
+                    A4_TRACE(6);
                     if (__any_sync(0xffffffffu, need)) {
                         uint32_t o[32];
                         tmem_ld32(t_o, o);
@@ -313,6 +344,7 @@ attn4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full[t]);
+                A4_TRACE(7);
                 l_run += l_lo + l_hi;
             };
 #pragma unroll 1

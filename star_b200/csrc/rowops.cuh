@@ -290,20 +290,8 @@ gn_stats2_kernel(const __half* __restrict__ x, double* __restrict__ stats, long 
         if (active) {
             const __half* xs = x + (sample * rows_per_sample) * C + oc * 8;
             long long r = r0 + ln;
-            for (; r + 7ll * lanes < r1; r += 8ll * lanes) {          // 8 independent 16-byte loads in flight (ncu round 1: 4 loads
-                uint4 u[8];                                            // left the kernel at 51 % DRAM with 16 long-scoreboard
-#pragma unroll                                                         // stall cycles per issue)
-                for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + (long long)k * lanes) * C));
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float f[8];
-                    unpack8(u[k], f);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
-                }
-            }
-            for (; r + 3ll * lanes < r1; r += 4ll * lanes) {
-                uint4 u[4];
+            for (; r + 3ll * lanes < r1; r += 4ll * lanes) {          // 4 independent 16-byte loads in flight (8 measured slower:
+                uint4 u[4];                                            // profiles/r02_kbench_gn_loads_ab.log)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xs + (r + (long long)k * lanes) * C));
 #pragma unroll
@@ -363,13 +351,6 @@ gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __h
         const long long r1 = min(rows_per_sample, r0 + GN2_SLAB);
         const long long base = (sample * rows_per_sample) * C + oc * 8;
         long long r = r0 + ln;
-        for (; r + 7ll * lanes < r1; r += 8ll * lanes) {
-            uint4 u[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + (r + (long long)k * lanes) * C));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) apply(u[k], out + base + (r + (long long)k * lanes) * C);
-        }
         for (; r + 3ll * lanes < r1; r += 4ll * lanes) {
             uint4 u[4];
 #pragma unroll

@@ -823,6 +823,18 @@ int star_debug_read_trace(long long* host_dst, int* host_counts) {
 }
 #endif
 
+#if STAR_ATTN_TRACE
+// experiment builds only (tools/attn_trace.py): softmax-phase timelines of CTA (0,0,0) of the spatial-attention kernel
+int star_debug_read_attn_trace(long long* host_dst, int* host_counts) {
+    STAR_CUDA(cudaDeviceSynchronize());
+    STAR_CUDA(cudaMemcpyFromSymbol(host_dst, g_a4_trace, sizeof(long long) * 2 * 8192));
+    STAR_CUDA(cudaMemcpyFromSymbol(host_counts, g_a4_trace_n, sizeof(int) * 2));
+    int zero[2] = {0, 0};
+    STAR_CUDA(cudaMemcpyToSymbol(g_a4_trace_n, zero, sizeof(zero)));
+    return 0;
+}
+#endif
+
 int star_sinusoidal(const void* t_i64, void* out, int B, int dim, void* stream) {
     const int n = B * (dim / 2);
     sinusoidal_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)t_i64, (__half*)out, B, dim);
