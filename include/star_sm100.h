@@ -85,9 +85,23 @@ int star_temporal_attention(const void* QKV, long long ld, void* O, long long ld
 
 /* GroupNorm(32) (+SiLU): nsamples blocks of rows_per_sample rows share statistics -- one frame for the 4-D norms
  * (unet_v2v.py:268,:610,:635,:1551), the whole clip for the 5-D norms (:1002,:1210-1219). fp32 statistics. */
+/* Causal Conv3d 3x3x3 of the CogVideoX 3-D VAE: replaces ContextParallelCausalConv3d.forward
+ * (cogvideox-based/sat/vae_modules/cp_enc_dec.py:384-430, the F.pad + Conv3d at :426-428).  X holds T + 2 frames of H x W x Cin
+ * tokens: the two leading frames are the temporal context the reference concatenates (:265-268 -- copies of frame 0, or the
+ * cache kept from the previous latent chunk), the spatial zero padding is implicit.  W27 [Cout, 3, 3, 3, Cin] (t, h, w). */
+int star_conv3d_causal(const void* X, const void* W27, const void* bias, const void* residual, long long ldres, void* out,
+                       long long ldo, int T, int H, int W, int Cin, int Cout, void* stream);
+
 long long star_groupnorm_workspace_bytes(int nsamples, int C);
 int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out, int nsamples,
                    long long rows_per_sample, int C, float eps, int silu, void* workspace, void* stream);
+/* SpatialNorm3D.forward of the CogVideoX 3-D VAE decoder (cp_enc_dec.py:491-510): out = GroupNorm32(X) * Ymod[src] + Bmod[src]
+ * (+ SiLU, the `nonlinearity` that always follows, :673,:687,:977) over one clip of T x H x W rows.  Ymod / Bmod are conv_y(zq) /
+ * conv_b(zq) evaluated at the latent's resolution (Tl, Hl, Wl): 1x1x1 convolutions commute with the nearest-neighbour
+ * interpolation of zq (:492-500, incl. its first-frame split for odd T); ldmod = their row pitch.  workspace: star_groupnorm_workspace_bytes(1, C). */
+int star_groupnorm_mod(const void* X, const void* gamma, const void* beta, const void* Ymod, const void* Bmod, long long ldmod,
+                       void* out, int T, int H, int W, int Tl, int Hl, int Wl, int C, float eps, int silu, void* workspace, void* stream);
+
 /* LayerNorm over C (unet_v2v.py:448-450) with fused LIEM gate: gate_mode 0 none, 1 per-row gate[] (spatial LIEM),
  * 2 temporal LIEM sigmoid(w0*max + w1*mean) (unet_v2v.py:396-411). */
 int star_layernorm(const void* X, const void* gamma, const void* beta, void* out, long long rows, int C, float eps,

@@ -272,10 +272,14 @@ def conv2d_3x3_s2p(x, w9, bias=None, pad=(0, 1, 0, 1)):
     return y.permute(0, 2, 3, 1).reshape(BT * Ho * Wo, -1).to(HALF), Ho, Wo
 
 
-def upsample2x(x, BT, H, W):
+def upsample2x(x, BT, H, W, out=None):
     C = x.shape[1]
     up = x.reshape(BT, H, W, C).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
-    return up.reshape(-1, C).contiguous()
+    up = up.reshape(-1, C).contiguous()
+    if out is not None:
+        out.copy_(up)
+        return out
+    return up
 
 
 def softmax_rows(s, cols):
@@ -320,3 +324,44 @@ def adain_color_fix(video, source, uint8=False):
         outs.append((c - cm) / cs * ss + sm)
     res = torch.cat(outs).clamp_(0.0, 1.0).permute(0, 2, 3, 1) * 255
     return res.round().to(torch.uint8) if uint8 else res
+
+
+def conv3d_causal(xp, w27, T, H, W, bias=None, residual=None, out=None):
+    """xp [(T+2)*H*W, Cin] (two context frames + clip); w27 [Cout, 3(t), 3(h), 3(w), Cin]"""
+    Cin = xp.shape[1]
+    x5 = _f(xp).reshape(1, T + 2, H, W, Cin).permute(0, 4, 1, 2, 3)
+    y = F.conv3d(x5, _f(w27).permute(0, 4, 1, 2, 3), _f(bias), padding=(0, 1, 1))
+    y = y.permute(0, 2, 3, 4, 1).reshape(T * H * W, -1)
+    if residual is not None:
+        y = y + _f(residual)
+    res = y.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def spatial_norm_src_index(T, H, W, Tl, Hl, Wl, device):
+    """row (t, h, w) -> latent row, the nearest-neighbour rule of SpatialNorm3D.forward (cp_enc_dec.py:492-500)"""
+    t = torch.arange(T, device=device)
+    if T > 1 and T % 2 == 1:
+        ts = torch.where(t == 0, torch.zeros_like(t), 1 + ((t - 1) * (Tl - 1)) // max(T - 1, 1))
+    else:
+        ts = (t * Tl) // T
+    hs = (torch.arange(H, device=device) * Hl) // H
+    ws = (torch.arange(W, device=device) * Wl) // W
+    return ((ts[:, None, None] * Hl + hs[None, :, None]) * Wl + ws[None, None, :]).reshape(-1)
+
+
+def groupnorm_mod(x, gamma, beta, ymod, bmod, T, H, W, Tl, Hl, Wl, eps, silu, out=None):
+    rows, C = x.shape
+    y = F.group_norm(_f(x).t().reshape(1, C, rows), 32, _f(gamma), _f(beta), eps).reshape(C, rows).t()
+    src = spatial_norm_src_index(T, H, W, Tl, Hl, Wl, x.device)
+    y = y * _f(ymod)[src] + _f(bmod)[src]
+    if silu:
+        y = F.silu(y)
+    res = y.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res

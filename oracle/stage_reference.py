@@ -10,7 +10,8 @@ are applied at load time exactly as in the container.
     python -m oracle.stage_reference            # idempotent; prints what it staged
 
 Files (relative to /root/reference): the model surface, the sampler, the helpers of the pipeline file and the
-tiny utils the sampler imports.  The CogVideoX files are staged for oracle/cogvideox_sat.py (sat shim layer).
+tiny utils the sampler imports.  The CogVideoX files are staged for oracle/cogvideox_sat.py (sat shim layer) and
+oracle/cogvideox_vae.py (3-D VAE decoder).
 """
 import os
 import shutil
@@ -34,6 +35,7 @@ FILES = [
     "cogvideox-based/transformer.py",
     "cogvideox-based/sat/dit_video_concat.py",
     "cogvideox-based/sat/sgm/modules/diffusionmodules/util.py",
+    "cogvideox-based/sat/vae_modules/cp_enc_dec.py",
 ]
 
 

@@ -362,6 +362,62 @@ gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __h
     }
 }
 
+// GroupNorm apply of the CogVideoX 3-D VAE's SpatialNorm3D (cp_enc_dec.py:451-510): y = GN(x) * Y[src] + B[src] (+ SiLU), where
+// Y = conv_y(zq), B = conv_b(zq) are 1x1x1 convolutions of the latent and therefore commute with the nearest-neighbour
+// interpolation of zq to the feature size: they are evaluated ONCE at latent resolution (Tl, Hl, Wl) and gathered per row.
+// Row r = (t, h, w) of the (T, H, W) clip reads latent row (ts, h*Hl/H, w*Wl/W); ts follows the reference's split of the first
+// frame when T is odd (> 1): ts = 0 for t = 0, else 1 + (t-1)(Tl-1)/(T-1); otherwise ts = t*Tl/T.  One sample (B = 1).
+struct GnModGeom {
+    int T, H, W, Tl, Hl, Wl, split_first;
+};
+
+__global__ void __launch_bounds__(GN2_THREADS)
+gn_apply_mod_kernel(const __half* __restrict__ x, const float* __restrict__ ab, const __half* __restrict__ ymod,
+                    const __half* __restrict__ bmod, long long ldmod, __half* __restrict__ out, long long rows, int C, int silu,
+                    Gn2Range rg, GnModGeom gm) {
+    const int O = C / 8;
+    const int lanes = GN2_THREADS / O;
+    const int tid = threadIdx.x;
+    const int oc = tid % O, ln = tid / O;
+    if (ln >= lanes) return;
+    long long g0, g1;
+    rg.span(g0, g1);
+    float a[8], b[8];
+    {
+        const float4* abp = reinterpret_cast<const float4*>(ab + (oc * 8) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 q = __ldg(abp + j);
+            a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
+        }
+    }
+    const int HW = gm.H * gm.W;
+    for (long long g = g0; g < g1; ++g) {
+        const long long r0 = g * GN2_SLAB;
+        const long long r1 = min(rows, r0 + GN2_SLAB);
+        for (long long r = r0 + ln; r < r1; r += lanes) {
+            const int t = (int)(r / HW);
+            const int hw = (int)(r - (long long)t * HW);
+            const int h = hw / gm.W, w = hw - h * gm.W;
+            int ts;
+            if (gm.split_first) ts = t == 0 ? 0 : 1 + (int)(((long long)(t - 1) * (gm.Tl - 1)) / (gm.T - 1));
+            else ts = (int)(((long long)t * gm.Tl) / gm.T);
+            const long long src = ((long long)ts * gm.Hl + (h * gm.Hl) / gm.H) * gm.Wl + (w * gm.Wl) / gm.W;
+            float f[8], fy[8], fb[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + oc * 8)), f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(ymod + src * ldmod + oc * 8)), fy);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(bmod + src * ldmod + oc * 8)), fb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = fmaf(fmaf(f[j], a[j], b[j]), fy[j], fb[j]);
+                if (silu) y = silu_f(y);
+                f[j] = y;
+            }
+            *reinterpret_cast<uint4*>(out + r * C + oc * 8) = pack8(f);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ LayerNorm over C with fused LIEM gate
 // gate_mode 0: y = LN(x)
 // gate_mode 1: y = LN(x * gate[row])            spatial LIEM, gate from liem_spatial_gate (unet_v2v.py:468-473)

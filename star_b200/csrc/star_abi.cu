@@ -489,6 +489,37 @@ int star_conv_t3(const void* X, const void* W3, const void* bias, const void* re
     return launch_tapgemm(d, (cudaStream_t)stream);
 }
 
+// Causal Conv3d 3x3x3 of the CogVideoX 3-D VAE (cogvideox-based/sat/vae_modules/cp_enc_dec.py:360-430): X holds T + 2 frames --
+// the two frames the reference concatenates in front of the clip (copies of frame 0, or the cache of the previous latent
+// chunk, :265-268) followed by the T frames of the clip -- so output frame t reads input frames t, t+1, t+2; the spatial
+// zero padding is the TMA out-of-bounds fill.  W27 is [Cout, 3(t), 3(h), 3(w), Cin].
+int star_conv3d_causal(const void* X, const void* W27, const void* bias, const void* residual, long long ldres, void* out,
+                       long long ldo, int T, int H, int W, int Cin, int Cout, void* stream) {
+    STAR_CHECK_INIT();
+    if (Cin % 8) return fail("star_conv3d_causal: Cin must be a multiple of 8");
+    TapDesc d;
+    memset(&d, 0, sizeof(d));
+    d.A = X;
+    d.adim[0] = Cin; d.adim[1] = W; d.adim[2] = H; d.adim[3] = T + 2; d.adim[4] = 1;
+    d.astr[1] = Cin; d.astr[2] = (unsigned long long)Cin * W; d.astr[3] = (unsigned long long)Cin * W * H;
+    d.astr[4] = (unsigned long long)Cin * W * H * (T + 2);
+    d.on[0] = W; d.on[1] = H; d.on[2] = T; d.on[3] = 1;
+    int th = 1, tw = 1;
+    best_box_2d(H, W, &th, &tw);
+    d.box[0] = tw; d.box[1] = th; d.box[2] = std::max(1, std::min(T, TG_BM / (tw * th))); d.box[3] = 1;
+    d.ntaps = 27;
+    for (int q = 0; q < 3; ++q)
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+                int* tp = d.tap[(q * 3 + r) * 3 + s];
+                tp[0] = s - 1; tp[1] = r - 1; tp[2] = q;
+            }
+    d.K = Cin; d.N = Cout;
+    d.W = W27; d.bias = bias; d.residual = residual; d.ldres = ldres;
+    d.out = out; d.ldo = ldo;
+    return launch_tapgemm(d, (cudaStream_t)stream);
+}
+
 long long star_conv2d_c4_workspace_bytes(int BT, int H, int W, int Cout) {
     return ((long long)BT * H * W * 64 + (long long)Cout * 64) * 2;
 }
@@ -614,6 +645,40 @@ int star_groupnorm(const void* X, const void* gamma, const void* beta, void* out
     gn_apply_kernel<<<grid_for(total_rows * (C / 8), 256), 256, 0, st>>>((const __half*)X, ab, (__half*)out, rows_per_sample,
                                                                           total_rows, C, silu);
     STAR_LAUNCH_CHECK("gn_apply");
+    return 0;
+}
+
+// SpatialNorm3D of the CogVideoX 3-D VAE decoder (cp_enc_dec.py:451-510): out = GroupNorm32(X) * Ymod[src] + Bmod[src] (+ SiLU)
+// over ONE clip of T x H x W rows; Ymod / Bmod = conv_y(zq) / conv_b(zq) at latent resolution (Tl, Hl, Wl) (see
+// gn_apply_mod_kernel), row pitch ldmod.  Workspace: star_groupnorm_workspace_bytes(1, C).
+int star_groupnorm_mod(const void* X, const void* gamma, const void* beta, const void* Ymod, const void* Bmod, long long ldmod,
+                       void* out, int T, int H, int W, int Tl, int Hl, int Wl, int C, float eps, int silu, void* workspace, void* stream) {
+    if (C % 32) return fail("star_groupnorm_mod: C must be a multiple of 32");
+    if (C / 8 > GN2_THREADS) return fail("star_groupnorm_mod: C too large");
+    if (H % Hl || W % Wl) return fail("star_groupnorm_mod: feature size must be a multiple of the latent size");
+    if (ldmod % 8 || ldmod < C) return fail("star_groupnorm_mod: ldmod must be a multiple of 8 and >= C");
+    const bool split = T > 1 && (T & 1);
+    if (split ? ((T - 1) % std::max(1, Tl - 1) != 0 || Tl < 2) : (T % Tl != 0))
+        return fail("star_groupnorm_mod: T=%d is not an integer multiple of the latent T=%d", T, Tl);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* stats = (double*)workspace;
+    float* ab = (float*)((char*)workspace + (size_t)32 * 2 * 8);
+    STAR_CUDA(cudaMemsetAsync(stats, 0, (size_t)32 * 2 * 8, st));
+    const long long rows = (long long)T * H * W;
+    Gn2Range rg;
+    rg.slabs_per_sample = (rows + GN2_SLAB - 1) / GN2_SLAB;
+    rg.total_slabs = rg.slabs_per_sample;
+    const int lanes2 = GN2_THREADS / (C / 8);
+    const size_t smem2 = (size_t)lanes2 * C * 2 * sizeof(float);
+    const unsigned grid2 = (unsigned)std::min<long long>(rg.total_slabs, (long long)num_sms() * 8);
+    gn_stats2_kernel<<<grid2, GN2_THREADS, smem2, st>>>((const __half*)X, stats, rows, C, rg);
+    STAR_LAUNCH_CHECK("gn_stats2");
+    gn_finalize_kernel<<<1, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows, C, eps);
+    STAR_LAUNCH_CHECK("gn_finalize");
+    GnModGeom gm{T, H, W, Tl, Hl, Wl, split ? 1 : 0};
+    gn_apply_mod_kernel<<<grid2, GN2_THREADS, 0, st>>>((const __half*)X, ab, (const __half*)Ymod, (const __half*)Bmod,
+                                                       ldmod, (__half*)out, rows, C, silu, rg, gm);
+    STAR_LAUNCH_CHECK("gn_apply_mod");
     return 0;
 }
 

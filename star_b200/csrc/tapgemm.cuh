@@ -6,6 +6,8 @@
 //   * Conv2d 3x3 (stride 1, pad 1)      : 9 taps over (h, w)    (unet_v2v.py:612, :639)
 //   * Conv2d 3x3 stride 2 pad (2,1)     : 9 taps over 4 parity planes (unet_v2v.py:709-722)
 //   * Conv3d (3,1,1) temporal conv      : 3 taps over t         (unet_v2v.py:1209-1220)
+//   * causal Conv3d 3x3x3               : 27 taps over (t, h, w) of a clip stored with two leading frames
+//                                         (cogvideox-based/sat/vae_modules/cp_enc_dec.py:360-430)
 // The A operand is addressed through a rank-5 TMA tensor map (C, n1, n2, n3, n4); an
 // M-tile is a box of <=128 "pixels"; each tap is a coordinate shift and out-of-bounds
 // coordinates are zero-filled by TMA, which implements the conv zero padding and the
@@ -23,7 +25,7 @@ namespace star {
 constexpr int TG_BM = 128;      // rows (pixels) per tile == TMEM lanes
 constexpr int TG_BK = 64;       // fp16 K elements per stage == 128 B swizzle span
 constexpr int TG_STAGES = 3;
-constexpr int TG_MAX_TAPS = 9;
+constexpr int TG_MAX_TAPS = 27;   // 3x3x3 causal Conv3d of the CogVideoX VAE (cp_enc_dec.py:360-430)
 constexpr int TG_THREADS = 192;
 
 enum TapGemmFlags : int {

@@ -202,6 +202,45 @@ def conv_t3(x, w3, bias=None, residual=None, B=1, T=1, HW=1, out=None):
 
 
 @_traced
+def conv3d_causal(xp, w27, T, H, W, bias=None, residual=None, out=None):
+    """Causal Conv3d 3x3x3 (CogVideoX VAE).  xp [(T+2)*H*W, Cin]: two context frames + the clip; w27 [Cout, 3, 3, 3, Cin];
+    returns [T*H*W, Cout]."""
+    _dev(xp)
+    rows, Cin = xp.shape
+    assert rows == (T + 2) * H * W and xp.is_contiguous() and w27.is_contiguous() and tuple(w27.shape[1:]) == (3, 3, 3, Cin)
+    _h(w27, "w27"); _h(bias, "bias"); _h(residual, "residual")
+    Cout = w27.shape[0]
+    if out is None:
+        out = torch.empty((T * H * W, Cout), dtype=_dt(), device=xp.device)
+    ldres = _rowmajor(residual, "residual") if residual is not None else 0
+    L = _lib()
+    _L.check(L.star_conv3d_causal(_p(xp), _p(w27), _p(bias), _p(residual), ldres, _p(out), _rowmajor(out, "out"),
+                                  T, H, W, Cin, Cout, _st()), "star_conv3d_causal")
+    return out
+
+
+@_traced
+def groupnorm_mod(x, gamma, beta, ymod, bmod, T, H, W, Tl, Hl, Wl, eps, silu, out=None):
+    """SpatialNorm3D: GroupNorm32 over one clip x [T*H*W, C], times ymod[src] plus bmod[src] (latent-resolution
+    [Tl*Hl*Wl, C] tables, nearest-neighbour gather with the reference's first-frame split), optional SiLU."""
+    _dev(x)
+    rows, C = x.shape
+    assert rows == T * H * W and x.is_contiguous()
+    assert tuple(ymod.shape) == (Tl * Hl * Wl, C) and tuple(bmod.shape) == (Tl * Hl * Wl, C)
+    ldmod = _rowmajor(ymod, "ymod")                      # column slices of one [rows, 2C] GEMM result are fine
+    assert _rowmajor(bmod, "bmod") == ldmod
+    _h(gamma, "gamma"); _h(beta, "beta"); _h(ymod, "ymod"); _h(bmod, "bmod")
+    L = _lib()
+    ws = torch.empty(L.star_groupnorm_workspace_bytes(1, C), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape and out.dtype == x.dtype
+    _L.check(L.star_groupnorm_mod(_p(x), _p(gamma), _p(beta), _p(ymod), _p(bmod), ldmod, _p(out), T, H, W, Tl, Hl, Wl, C,
+                                  float(eps), int(bool(silu)), _p(ws), _st()), "star_groupnorm_mod")
+    return out
+
+
+@_traced
 def conv2d_3x3_c4(x, w9, bias=None, residual=None):
     """Stem conv, x [BT, H, W, 4]; w9 [Cout, 3, 3, 4]."""
     _dev(x)
@@ -314,12 +353,14 @@ def upsample2x_crop(x, BT, H, W):
 
 
 @_traced
-def upsample2x(x, BT, H, W):
+def upsample2x(x, BT, H, W, out=None):
     """plain nearest x2: [BT*H*W, C] -> [BT*2H*2W, C]"""
     _dev(x)
     C = x.shape[1]
     assert x.is_contiguous()
-    out = torch.empty((BT * 4 * H * W, C), dtype=_dt(), device=x.device)
+    if out is None:
+        out = torch.empty((BT * 4 * H * W, C), dtype=_dt(), device=x.device)
+    assert out.is_contiguous() and tuple(out.shape) == (BT * 4 * H * W, C)
     L = _lib()
     _L.check(L.star_upsample2x(_p(x), _p(out), BT, H, W, C, 0, _st()), "star_upsample2x")
     return out

@@ -49,6 +49,53 @@ def main():
     print("  ops:", ", ".join(f"{k} {v:.2f} ms ({100 * v / tot:.0f}%)" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])))
 
 
+def vae3d_leg(dev, dtype, T, H, W, step_ms):
+    """the decode tail of config 4 (sample_sr.py:206-230): 13 latent frames of 60x90 -> 49 frames of 480x720 through the 3-D
+    causal VAE decoder in the reference's chunk protocol (3 + 5 x 2 latent frames), causal-conv context kept on the GPU"""
+    from star_b200.cogvideox.vae3d import ContextParallelDecoder3D
+    from star_b200.utils.synth import synth_tensor
+    with torch.device("meta"):
+        dec = ContextParallelDecoder3D()
+    sd = {k: synth_tensor(k, v.shape, 11, dev) + (1.0 if ".conv_y.conv.bias" in k else 0.0) for k, v in dec.state_dict().items()}
+    dec.load_state_dict(sd, assign=True)
+    dec = dec.to(dtype).eval()
+    z = torch.randn(1, 16, T, H, W, generator=torch.Generator().manual_seed(5)).to(dev, dtype)
+    frames = dec.decode_latent(z)                                   # warm-up (packs the weights)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    n0 = ops.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(2):
+        frames = dec.decode_latent(z)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 2
+    nf = frames.shape[2]
+    # 27-tap convs dominate: 2 * rows * 27 * Cin * Cout summed over the decoder, per clip
+    flops = 0.0
+    chans = {3: (512, 512), 2: (512, 256), 1: (256, 256), 0: (256, 128)}
+    for (t_l, first) in [(3, True)] + [(2, False)] * ((T - 1) // 2 - 1):
+        tt, hh, ww = t_l, H, W
+        flops += 2.0 * tt * hh * ww * 27 * 64 * 512 + 2 * 2 * 2.0 * tt * hh * ww * 27 * 512 * 512
+        for lvl in (3, 2, 1, 0):
+            cin, cout = chans[lvl]
+            rows = tt * hh * ww
+            flops += 2.0 * rows * 27 * (cin * cout + cout * cout) + 3 * 2 * 2.0 * rows * 27 * cout * cout
+            if lvl:
+                if lvl >= 2:
+                    tt = 2 * tt - 1 if (tt % 2 == 1 and tt > 1) else 2 * tt
+                hh, ww = 2 * hh, 2 * ww
+                flops += 2.0 * tt * hh * ww * 9 * cout * cout
+        flops += 2.0 * tt * hh * ww * 27 * 128 * 3
+    return {"what": "CogVideoX 3-D causal VAE decode of the clip (SURVEY 8 f4), reference chunk protocol, context frames on the GPU",
+            "frames": int(nf), "decode_ms_per_clip": ms, "decode_ms_per_frame": ms / nf, "decode_tflops_per_s": flops / ms / 1e9,
+            "algorithmic_tflop_per_clip": flops / 1e12, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "launches_per_clip": int((ops.launch_count() - n0) // 2), "finite": bool(torch.isfinite(frames.float()).all()),
+            "frames_per_s_denoise_plus_decode": nf / ((50 * step_ms + ms) / 1e3),
+            "parity": "tests/test_cogvideox_vae.py (reference's unmodified cp_enc_dec.py)"}
+
+
 def run_config4(args):
     """bench.py --workload cogvideox: BASELINE config 4 -- CogVideoX-5B heavy-deg 4x, 49 frames 720x480 (latent 13 x 60 x 90,
     patch 2 -> 17 550 image + 226 text tokens), the whole 42-layer DiffusionTransformer with LoRA r = 512 merged, bf16 (the
@@ -145,6 +192,9 @@ def run_config4(args):
     clips = (world // 2) if split else world                   # replicas beyond the CFG pair (different clips in production)
     d, ff = 3072, 4 * 3072
     layer_flops = 2 * (2.0 * S * d * 3 * d + 2.0 * S * d * d + 4.0 * S * d * ff) + 2 * 4.0 * S * S * d   # both CFG branches
+    vae_leg = None
+    if world == 1 and not args.small:
+        vae_leg = vae3d_leg(dev, dtype, T, H, W, ms)
     if rank == 0:
         line = {"metric": "upscaled frames/sec, CogVideoX-5B heavy-deg 4x, 49-frame 720x480, 50 steps", "value": 49.0 / (50 * ms / 1e3),
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -167,6 +217,7 @@ def run_config4(args):
                 "model_tflops_per_s": layers * layer_flops * (bsz / 2.0) / (ms * 1e-3) / 1e12,
                 "op_time_share": {k: round(v / sum(per_op.values()), 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])},
                 "out_checksum": {"finite": bool(torch.isfinite(out).all()), "abs_mean": float(out.abs().mean())},
+                "pipeline": vae_leg,
                 "parity": "tests/test_cogvideox.py::test_dit_model_gpu_vs_reference_files (reference files behind the sat shim)"}
         print(json.dumps(line), flush=True)
     if world > 1:
