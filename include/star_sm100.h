@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define STAR_FLAG_GEGLU 1     /* W has 2N rows (value|gate): out = value * gelu_erf(gate)  (unet_v2v.py:496-504) */
+#define STAR_FLAG_GELU_ERF 4  /* out = gelu_erf(acc) (nn.GELU of the OpenCLIP text tower's MLP, video_to_video/modules/embedder.py:27)    */
 #define STAR_FLAG_GELU_TANH 8 /* out = gelu_tanh(acc) (sat MLP activation, cogvideox-based/transformer.py:202-312)  */
 #define STAR_FLAG_SILU_OUT 2  /* out = silu(acc)                                            (unet_v2v.py:1340-1342) */
 
@@ -78,6 +79,12 @@ int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const vo
  * xformers.ops.memory_efficient_attention at unet_v2v.py:179,:184 for spatial self- and text cross-attention. */
 int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
                    long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, void* stream);
+/* Causal self-attention, head_dim 64: query i attends keys 0..i.  Replaces nn.MultiheadAttention with the text tower's
+ * attn_mask inside the OpenCLIP ViT-H-14 residual blocks FrozenOpenCLIPEmbedder.text_transformer_forward iterates
+ * (video_to_video/modules/embedder.py:56-71; mask = open_clip's build_attention_mask, -inf above the diagonal). */
+int star_attention_causal(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                          long long ldo, int batch, int heads, int N, float scale, void* stream);
+
 /* Temporal self-attention over T frames per pixel; QKV [B*T*HW, ld] with q|k|v at column 0|Ci|2Ci
  * (unet_v2v.py:483-489 through :158-195). */
 int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,

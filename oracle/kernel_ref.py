@@ -21,6 +21,7 @@ def set_dtype(dtype):
     HALF = dtype
 
 FLAG_SILU_OUT = 2
+FLAG_GELU_ERF = 4
 
 
 def _f(t):
@@ -34,6 +35,8 @@ def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, o
     if flags & FLAG_GEGLU:
         val, gate = acc.chunk(2, dim=-1)
         acc = val * F.gelu(gate)
+    if flags & FLAG_GELU_ERF:
+        acc = F.gelu(acc)
     if rowvec is not None:
         idx = torch.arange(a.shape[0], device=a.device) // rowvec_div
         acc = acc + _f(rowvec)[idx]
@@ -42,6 +45,19 @@ def linear(a, w, bias=None, residual=None, rowvec=None, rowvec_div=1, flags=0, o
     if flags & FLAG_SILU_OUT:
         acc = F.silu(acc)
     res = acc.to(HALF)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def attention_causal(q, k, v, batch, heads, N, scale=0.125, out=None):
+    def split(t):
+        return _f(t)[:, :heads * 64].reshape(batch, N, heads, 64).permute(0, 2, 1, 3)
+    s = (split(q) @ split(k).transpose(-1, -2)) * scale
+    s = s + torch.full((N, N), float("-inf"), device=q.device).triu(1)
+    o = torch.softmax(s, dim=-1) @ split(v)
+    res = o.permute(0, 2, 1, 3).reshape(batch * N, heads * 64).to(HALF)
     if out is not None:
         out.copy_(res)
         return out

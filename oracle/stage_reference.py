@@ -36,6 +36,14 @@ FILES = [
     "cogvideox-based/sat/dit_video_concat.py",
     "cogvideox-based/sat/sgm/modules/diffusionmodules/util.py",
     "cogvideox-based/sat/vae_modules/cp_enc_dec.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/sampling_utils.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/guiders.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/discretizer.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/denoiser_scaling.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/denoiser_weighting.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/denoiser.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/wrappers.py",
+    "cogvideox-based/sat/sgm/modules/diffusionmodules/sampling.py",
 ]
 
 

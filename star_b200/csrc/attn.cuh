@@ -1,6 +1,6 @@
 // star_b200 / csrc / attn.cuh
 // Flash-style attention forward for head_dim 64, fp16 in / fp32 softmax + accumulate:
-//     O = softmax(Q K^T * scale) V          (no mask, no bias)
+//     O = softmax(Q K^T * scale) V          (no bias; optional causal mask for the text tower)
 // replaces xformers.ops.memory_efficient_attention at unet_v2v.py:179/:184 for the
 // spatial self-attention (N = H*W up to 26 352) and the text cross-attention (Nk = 77).
 //
@@ -28,6 +28,7 @@ constexpr int AT_THREADS = 192;
 
 struct AttnParams {
     int Nq, Nk;
+    int causal;             // 1: query row q attends keys 0..q only (text tower); honoured by attn_fwd_kernel, not by attn4
     int kv_batch_div;       // kv batch index = q batch index / kv_batch_div (text context shared by the frames of a clip)
     float scale_log2;       // softmax scale * log2(e)
     __half* out;
@@ -199,7 +200,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < nt; ++j) {
             const int b = j & 1;
             const int kbase = j * AT_BKV;
-            const bool tail = (kbase + AT_BKV > p.Nk);
+            const int klim = p.causal ? min(p.Nk, q0 + r + 1) : p.Nk;      // keys [0, klim) are visible to this row
+            const bool tail = (kbase + AT_BKV > klim);
             mbar_wait(&s_full[b], (j >> 1) & 1);
             tc_fence_after();
             const uint32_t t_s = tmem_s0 + b * 128 + lane_off;
@@ -213,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float sv = __uint_as_float(v[i]);
-                    if (tail && kbase + c * 32 + i >= p.Nk) sv = -INFINITY;
+                    if (tail && kbase + c * 32 + i >= klim) sv = -INFINITY;
                     mx = fmaxf(mx, sv);
                 }
             }
@@ -235,8 +237,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     float p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new);
                     float p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new);
                     if (tail) {
-                        if (kbase + c * 32 + i >= p.Nk) p0 = 0.f;
-                        if (kbase + c * 32 + i + 1 >= p.Nk) p1 = 0.f;
+                        if (kbase + c * 32 + i >= klim) p0 = 0.f;
+                        if (kbase + c * 32 + i + 1 >= klim) p1 = 0.f;
                     }
                     // the row sum uses the fp16-rounded probabilities that the PV MMA consumes
                     __half2 h = __floats2half2_rn(p0, p1);

@@ -241,7 +241,7 @@ int launch_tapgemm2_bn(const TapDesc& d, cudaStream_t st) {
     ex.stages = TapGemm2Smem<BN>::stages(res_tma, ex.dbuf != 0);
     const size_t smem = TapGemm2Smem<BN>::total(res_tma, ex.dbuf != 0);
     // compile-time specialised epilogues for the three shapes that carry ~all of the linear / conv time
-    const bool extras = d.rowvec || d.colscale || (d.flags & (TG_GELU_TANH | TG_SILU_OUT));
+    const bool extras = d.rowvec || d.colscale || (d.flags & (TG_GELU_TANH | TG_GELU_ERF | TG_SILU_OUT));
     bool launched = false;
     if (geglu && !d.residual && !extras) {
         if constexpr (BN != 160) {
@@ -269,8 +269,8 @@ int launch_tapgemm(const TapDesc& d, cudaStream_t st) {
                          (!geglu || d.N % 64 == 0);
     // Non-persistent kernel (2 CTAs/SM, two interleaved MMA streams) is measurably faster for the long-reduction,
     // wide-N convolutions (profiles/r01_kbench_ab_experiments.txt); the persistent one wins everywhere else.
-    const bool v2_only = d.colscale != nullptr || (d.flags & TG_GELU_TANH);
-    if (v2_only && !aligned) return fail("tapgemm: colscale / tanh-GELU epilogues need N %% 32 == 0 and 16-byte aligned rows");
+    const bool v2_only = d.colscale != nullptr || (d.flags & (TG_GELU_TANH | TG_GELU_ERF));
+    if (v2_only && !aligned) return fail("tapgemm: colscale / GELU epilogues need N %% 32 == 0 and 16-byte aligned rows");
     const bool long_k = ((long long)d.ntaps * d.K >= 3840) && (d.N % 128 == 0) && !geglu && !v2_only;
     // 128x256 tiles (4 x 48 KB stages, two-pass epilogue): 25 % less L2->SM operand traffic per flop and N = 256 MMAs
     // (137 clk per instruction against a 128 clk floor; N = 128 retires at 73 against 64: profiles/r01_micro_mma_rate.log)
@@ -539,8 +539,9 @@ int star_conv2d_3x3_c4(const void* X, const void* W9, const void* bias, const vo
     return star_linear(col, 64, w64, bias, nullptr, 1, residual, Cout, out, Cout, rows, 64, Cout, 0, stream);
 }
 
-int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
-                   long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, void* stream) {
+static int attention_impl(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                          long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, int causal,
+                          void* stream) {
     STAR_CHECK_INIT();
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return fail("star_attention: leading dims must be multiples of 8");
     if (Nq <= 0 || Nk <= 0 || batch <= 0) return fail("star_attention: empty problem");
@@ -561,7 +562,7 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
         if (make_tmap(&tv, V, 3, dims, strv, box)) return 1;
     }
     AttnParams p;
-    p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div;
+    p.Nq = Nq; p.Nk = Nk; p.kv_batch_div = kv_batch_div; p.causal = causal;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__half*)O; p.ldo = ldo;
     if (heads > 65535 || batch > 65535) return fail("star_attention: grid too large");
@@ -569,7 +570,7 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     // Multi-tile problems (spatial self-attention): two 128-row query tiles per CTA, row-split softmax, every exponential on
     // the MUFU (in-step A/B on the full model: profiles/r01_bench_ab_attention.log).  Single-KV-tile problems (text
     // cross-attention, tiny latents): the one-tile kernel, two CTAs per SM.
-    if (Nk > AT_BKV && Nq > AT_BQ) {
+    if (Nk > AT_BKV && Nq > AT_BQ && !causal) {
         dim3 grid((Nq + 255) / 256, heads, batch);
         attn4_fwd_kernel<<<grid, A4S_THREADS, Attn4Smem::TOTAL, st>>>(tq, tk, tv, p);
         STAR_LAUNCH_CHECK("attn4_fwd");
@@ -580,6 +581,17 @@ int star_attention(const void* Q, long long ldq, const void* K, long long ldk, c
     else attn_fwd_kernel<false><<<grid, AT_THREADS, AttnSmemT<false>::TOTAL, st>>>(tq, tk, tv, p);
     STAR_LAUNCH_CHECK("attn_fwd");
     return 0;
+}
+
+int star_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                   long long ldo, int batch, int heads, int Nq, int Nk, int kv_batch_div, float scale, void* stream) {
+    return attention_impl(Q, ldq, K, ldk, V, ldv, O, ldo, batch, heads, Nq, Nk, kv_batch_div, scale, 0, stream);
+}
+
+// causal self-attention (query i attends keys 0..i): the text tower's attn_mask (embedder.py:57, open_clip build_attention_mask)
+int star_attention_causal(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                          long long ldo, int batch, int heads, int N, float scale, void* stream) {
+    return attention_impl(Q, ldq, K, ldk, V, ldv, O, ldo, batch, heads, N, N, 1, scale, 1, stream);
 }
 
 int star_temporal_attention(const void* QKV, long long ld, void* O, long long ldo, int B, int T, long long HW,

@@ -31,6 +31,7 @@ constexpr int TG_THREADS = 192;
 enum TapGemmFlags : int {
     TG_GEGLU = 1,        // W has 2N rows (value | gate); out = value * gelu_erf(gate)
     TG_SILU_OUT = 2,     // out = silu(acc)
+    TG_GELU_ERF = 4,     // out = gelu_erf(acc)   (nn.GELU of the OpenCLIP text tower's MLP, embedder.py:27)
     TG_GELU_TANH = 8,    // out = gelu_tanh(acc)  (CogVideoX MLP, sat default gelu)
 };
 

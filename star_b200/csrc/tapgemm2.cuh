@@ -134,6 +134,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const bool has_rowvec = GEN && p.rowvec != nullptr;
     const bool has_colscale = GEN && p.colscale != nullptr;
     const bool act_tanh = GEN && (p.flags & TG_GELU_TANH) != 0;
+    const bool act_erf = GEN && (p.flags & TG_GELU_ERF) != 0;
     const bool act_silu = GEN && (p.flags & TG_SILU_OUT) != 0;
     const int n_per_tile = geglu ? BN / 2 : BN;
     const int total_iters = p.ntaps * p.k_chunks;
@@ -393,6 +394,10 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (act_tanh) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_f(f[j]);
+                }
+                if (act_erf) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
                 }
                 if (has_colscale) {
 #pragma unroll

@@ -31,6 +31,7 @@ SIGNATURES = {
     "star_conv2d_c4_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "star_conv2d_3x3_c4": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "star_attention": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _f, _p]),
+    "star_attention_causal": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _f, _p]),
     "star_temporal_attention": (_i, [_p, _ll, _p, _ll, _i, _i, _ll, _i, _i, _f, _p]),
     "star_groupnorm_workspace_bytes": (_ll, [_i, _i]),
     "star_groupnorm": (_i, [_p, _p, _p, _p, _i, _ll, _i, _f, _i, _p, _p]),

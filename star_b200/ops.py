@@ -13,6 +13,7 @@ HALF = torch.float16
 
 FLAG_GEGLU = 1
 FLAG_SILU_OUT = 2
+FLAG_GELU_ERF = 4
 
 
 # ---- optional per-op tracing (CUDA events on the launching stream) ---------------------------------
@@ -265,6 +266,19 @@ def attention(q, k, v, batch, heads, Nq, Nk, kv_batch_div=1, scale=0.125, out=No
     L = _lib()
     _L.check(L.star_attention(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), _rowmajor(out, "out"), batch, heads,
                               Nq, Nk, kv_batch_div, float(scale), _st()), "star_attention")
+    return out
+
+
+@_traced
+def attention_causal(q, k, v, batch, heads, N, scale=0.125, out=None):
+    """causal self-attention (query i sees keys 0..i): q, k, v [batch*N, >=heads*64] strided 2-D views"""
+    _dev(q)
+    ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
+    if out is None:
+        out = torch.empty((batch * N, heads * 64), dtype=_dt(), device=q.device)
+    L = _lib()
+    _L.check(L.star_attention_causal(_p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), _rowmajor(out, "out"), batch, heads, N,
+                                     float(scale), _st()), "star_attention_causal")
     return out
 
 

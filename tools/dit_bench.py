@@ -88,7 +88,31 @@ def vae3d_leg(dev, dtype, T, H, W, step_ms):
                 hh, ww = 2 * hh, 2 * ww
                 flops += 2.0 * tt * hh * ww * 9 * cout * cout
         flops += 2.0 * tt * hh * ww * 27 * 128 * 3
+    # the reference's own decoder (unmodified cp_enc_dec.py from the staged tree) on the same GPU, same latent, same dtype
+    gpu_ref = None
+    try:
+        from oracle.cogvideox_vae import build_reference_decoder, reference_decode_latent, vae_reference_available
+        if vae_reference_available():
+            rdec = build_reference_decoder({k: v.float() for k, v in sd.items()}).to(dev, dtype)
+            del sd
+            reference_decode_latent(rdec, z)                              # warm-up (cuDNN autotune)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            rframes = reference_decode_latent(rdec, z)
+            r1.record()
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1)
+            diff = ((frames.float() - rframes.float()).norm() / rframes.float().norm()).item()
+            gpu_ref = {"decode_ms_per_clip": rms, "star_over_reference": rms / ms, "rel_l2_star_vs_reference_same_dtype": diff,
+                       "how": "ContextParallelDecoder3D of the reference tree, " + str(dtype) + ", cuDNN Conv3d, its CPU cache round trip included"}
+            del rdec, rframes
+        else:
+            gpu_ref = {"unavailable": "oracle/_ref not staged on this box"}
+    except Exception as e:                                                # the baseline must never break the bench line
+        gpu_ref = {"unavailable": repr(e)[:200]}
     return {"what": "CogVideoX 3-D causal VAE decode of the clip (SURVEY 8 f4), reference chunk protocol, context frames on the GPU",
+            "gpu_reference": gpu_ref,
             "frames": int(nf), "decode_ms_per_clip": ms, "decode_ms_per_frame": ms / nf, "decode_tflops_per_s": flops / ms / 1e9,
             "algorithmic_tflop_per_clip": flops / 1e12, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "launches_per_clip": int((ops.launch_count() - n0) // 2), "finite": bool(torch.isfinite(frames.float()).all()),
