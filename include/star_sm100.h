@@ -136,6 +136,11 @@ int star_concat_add(const void* a, int Ca, const void* b, const void* c, int Cb,
 int star_add(const void* a, const void* b, void* out, long long n, void* stream);
 /* nearest x2 + crop first/last row (unet_v2v.py:563-564): out [BT, 2H-2, 2W, C] */
 int star_upsample2x_crop(const void* X, void* out, int BT, int H, int W, int C, void* stream);
+/* Temporal half of DownSample3D.forward in the CogVideoX 3-D VAE encoder (cogvideox-based/sat/vae_modules/cp_enc_dec.py:581-596):
+ * avg_pool1d(kernel 2, stride 2) over the frames of a [(T HW), C] clip; odd T keeps the first frame and pools the other T - 1.
+ * out has ceil(T / 2) frames. */
+int star_time_avgpool2(const void* X, void* out, int T, long long HW, int C, void* stream);
+
 /* nearest x2, crop_rows = 1 as above, 0 = plain F.interpolate(scale_factor=2) of the VAE decoder's Upsample2D
  * (video_to_video_model.py:142 vae.decode): out [BT, 2H - 2*crop_rows, 2W, C] */
 int star_upsample2x(const void* X, void* out, int BT, int H, int W, int C, int crop_rows, void* stream);

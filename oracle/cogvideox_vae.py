@@ -98,3 +98,23 @@ def reference_decode_latent(dec, latent):
             a, b = (0, 3) if i == 0 else (2 * i + 1, 2 * i + 3)
             out.append(dec(latent[:, :, a:b].contiguous(), clear_fake_cp_cache=(i == loops - 1)))
     return torch.cat(out, dim=2)
+
+
+ENCODER_KW = dict(double_z=True, z_channels=16, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 2, 4),
+                  attn_resolutions=[], num_res_blocks=3, dropout=0.0, gather_norm=True)      # cogvideox_5b_infer_sr.yaml:113-126
+
+
+def build_reference_encoder(state_dict=None, **overrides):
+    m = load_reference_vae()
+    kw = dict(ENCODER_KW)
+    kw.update(overrides)
+    enc = m.ContextParallelEncoder3D(**kw)
+    if state_dict is not None:
+        enc.load_state_dict(state_dict)
+    return enc.eval()
+
+
+@torch.no_grad()
+def reference_encode_moments(enc, x):
+    with single_rank():
+        return enc(x)

@@ -381,3 +381,13 @@ def groupnorm_mod(x, gamma, beta, ymod, bmod, T, H, W, Tl, Hl, Wl, eps, silu, ou
         out.copy_(res)
         return out
     return res
+
+
+def time_avgpool2(x, T, HW):
+    C = x.shape[1]
+    f = _f(x).reshape(T, HW, C)
+    if T % 2:
+        out = torch.cat([f[:1], 0.5 * (f[1::2] + f[2::2])], 0)
+    else:
+        out = 0.5 * (f[0::2] + f[1::2])
+    return out.reshape(-1, C).to(HALF)

@@ -96,42 +96,47 @@ class VPSDEDPMPP2MSampler:
         self.plan = StepPlan(num_steps, 1000, shift_scale, cfg_scale, cfg_exp, cfg_steps)
 
     @torch.no_grad()
+    def step(self, network, x, old, st, context, lq=None):
+        """one solver step: DiT forward of the CFG pair, guidance, DPM-Solver++(2M) SDE update -> (x_next, denoised)"""
+        B = x.shape[0]
+        xin = torch.cat([x, x], 0)
+        if lq is not None:
+            xin = torch.cat((xin, lq.to(xin.dtype)), dim=2)
+        ts = torch.full((2 * B,), float(st.timestep), device=x.device, dtype=x.dtype)
+        out = network(xin, timesteps=ts, context=context)
+        x_u, x_c = (out.float() * st.c_out + xin[:, :, :x.shape[2]] * st.c_skip).chunk(2)  # Denoiser.forward: net * c_out + x * c_skip
+        denoised = x_u + st.cfg_scale * (x_c - x_u)                                    # NoDynamicThresholding (sampling_utils.py:8-11)
+        if st.last:
+            return denoised, denoised
+        noise = torch.randn_like(x)
+        if old is not None:
+            noise = torch.randn_like(x)                                                 # the reference draws twice, uses the second
+            d = st.mult3 * denoised - st.mult4 * old
+        else:
+            d = denoised
+        return st.mult1 * x - st.mult2 * d + st.mult_noise * noise, denoised
+
+    @torch.no_grad()
     def __call__(self, network, x, cond, uc=None, lq=None, callback=None):
         uc = cond if uc is None else uc
-        B = x.shape[0]
         context = torch.cat((uc["crossattn"], cond["crossattn"]), 0).to(self.dtype)        # unconditional branch first (guiders.py:47-49)
         x = x.float()
         old = None
         for i, st in enumerate(self.plan.steps):
-            xin = torch.cat([x, x], 0)
-            if lq is not None:
-                xin = torch.cat((xin, lq.to(xin.dtype)), dim=2)
-            ts = torch.full((2 * B,), float(st.timestep), device=x.device, dtype=x.dtype)
-            out = network(xin, timesteps=ts, context=context)
-            x_u, x_c = (out.float() * st.c_out + xin[:, :, :x.shape[2]] * st.c_skip).chunk(2)  # Denoiser.forward: net * c_out + x * c_skip
-            denoised = x_u + st.cfg_scale * (x_c - x_u)                                    # NoDynamicThresholding (sampling_utils.py:8-11)
-            if st.last:
-                x = denoised
-            else:
-                noise = torch.randn_like(x)
-                if old is not None:
-                    noise = torch.randn_like(x)                                             # the reference draws twice, uses the second
-                    d = st.mult3 * denoised - st.mult4 * old
-                else:
-                    d = denoised
-                x = st.mult1 * x - st.mult2 * d + st.mult_noise * noise
-            old = denoised
+            x, old = self.step(network, x, old, st, context, lq)
             if callback is not None:
                 callback(i, x)
         return x
 
 
 @torch.no_grad()
-def sample_sr_latent(network, sampler, cond, uc, lq_latent, generator_seed=None):
+def sample_sr_latent(network, sampler, cond, uc, lq_latent, generator_seed=None, randn=None):
     """the part of ``sample_sr`` (diffusion_video.py:245-292) after the LQ clip has been encoded: start noise of the LQ latent's
-    shape, the LQ latent doubled for the CFG pair, sampler -> latent in the model dtype"""
+    shape (drawn on the host like the reference, :256, unless given), the LQ latent doubled for the CFG pair, sampler -> latent in
+    the model dtype"""
     if generator_seed is not None:
         torch.manual_seed(generator_seed)
-    randn = torch.randn(lq_latent.shape, dtype=torch.float32).to(lq_latent.device)          # drawn on the host like the reference
+    if randn is None:
+        randn = torch.randn(lq_latent.shape, dtype=torch.float32).to(lq_latent.device)
     lq = torch.cat((lq_latent, lq_latent), dim=0)
     return sampler(network, randn, cond, uc=uc, lq=lq).to(sampler.dtype)

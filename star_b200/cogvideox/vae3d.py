@@ -1,5 +1,6 @@
-"""CogVideoX 3-D causal VAE *decoder* (cogvideox-based/sat/vae_modules/cp_enc_dec.py:839-983 ``ContextParallelDecoder3D``) on the
-star_b200 kernels -- SURVEY section 8 row f4: the decode tail of the CogVideoX path (sample_sr.py:206-230).
+"""CogVideoX 3-D causal VAE (cogvideox-based/sat/vae_modules/cp_enc_dec.py: ``ContextParallelDecoder3D`` :839-983 and, at the end
+of this file, ``ContextParallelEncoder3D`` :716-836) on the star_b200 kernels -- SURVEY section 8 row f4: the decode tail of the
+CogVideoX path (sample_sr.py:206-230) and the encode of the LQ clip in front of it (diffusion_video.py:279-282).
 
 Parameter tree = the reference decoder's (``first_stage_model.decoder.*`` of the 3d-vae checkpoint):
     conv_in.conv.*, conv_out.conv.*                                   ContextParallelCausalConv3d 3x3x3            (:360-430)
@@ -51,6 +52,26 @@ class _ResnetBlock3D(nn.Module):
         self.conv2 = _CausalConv3d(cout, cout, 3)
         if cin != cout:
             self.nin_shortcut = nn.Conv3d(cin, cout, 1)
+
+
+class _ResnetBlock3DPlain(nn.Module):
+    """encoder block: plain GroupNorm32 (``Normalize``, cp_enc_dec.py:444-448) instead of SpatialNorm3D"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(32, cin, eps=1e-6, affine=True)
+        self.conv1 = _CausalConv3d(cin, cout, 3)
+        self.norm2 = nn.GroupNorm(32, cout, eps=1e-6, affine=True)
+        self.conv2 = _CausalConv3d(cout, cout, 3)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv3d(cin, cout, 1)
+
+
+class _DownSample3D(nn.Module):
+    def __init__(self, c, compress_time):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+        self.compress_time = compress_time
 
 
 class _Upsample3D(nn.Module):
@@ -244,3 +265,136 @@ class ContextParallelDecoder3D(nn.Module):
             a, b = (0, 3) if i == 0 else (2 * i + 1, 2 * i + 3)
             out.append(self.forward(latent[:, :, a:b].contiguous(), clear_fake_cp_cache=(i == loops - 1)))
         return torch.cat(out, dim=2)
+
+
+class ContextParallelEncoder3D(nn.Module):
+    """``ContextParallelEncoder3D`` (cp_enc_dec.py:716-836) with the reference's constructor keywords and state-dict keys: the
+    encoder that turns the (bicubically pre-upsampled) LQ clip into the latent the DiT is conditioned on
+    (diffusion_video.py:279-283).  The whole clip is one call (no chunk protocol on this side): causal 27-tap convs with the first
+    frame replicated in front, clip-wide GroupNorm32 + SiLU written straight into the conv's input buffer, DownSample3D =
+    frame-pair average (first frame kept for odd T) + stride-2 conv with (0,1,0,1) padding.  ``forward`` returns the moments
+    (mean | logvar, 2 z_channels); ``encode`` applies DiagonalGaussianRegularizer (regularizers.py:84-104)."""
+
+    def __init__(self, *, ch=128, out_ch=3, ch_mult=(1, 2, 2, 4), num_res_blocks=3, attn_resolutions=(), dropout=0.0,
+                 resamp_with_conv=True, in_channels=3, resolution=256, z_channels=16, double_z=True, pad_mode="first",
+                 temporal_compress_times=4, gather_norm=False, **ignore_kwargs):
+        super().__init__()
+        if len(attn_resolutions) or not resamp_with_conv or not double_z:
+            raise NotImplementedError("only the shipped CogVideoX encoder configuration is built")
+        assert in_channels <= ZQ_PAD
+        self.in_channels, self.z_channels = in_channels, z_channels
+        self.num_resolutions = len(ch_mult)
+        tlevel = {1: 0, 2: 1, 4: 2, 8: 3}[temporal_compress_times]
+        self.conv_in = _CausalConv3d(in_channels, ch, 3)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        for i_level in range(self.num_resolutions):
+            down = nn.Module()
+            down.block, down.attn = nn.ModuleList(), nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[i_level], ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                down.block.append(_ResnetBlock3DPlain(block_in, block_out))
+                block_in = block_out
+            if i_level != self.num_resolutions - 1:
+                down.downsample = _DownSample3D(block_in, compress_time=i_level < tlevel)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = _ResnetBlock3DPlain(block_in, block_in)
+        self.mid.block_2 = _ResnetBlock3DPlain(block_in, block_in)
+        self.norm_out = nn.GroupNorm(32, block_in, eps=1e-6, affine=True)
+        self.conv_out = _CausalConv3d(block_in, 2 * z_channels, 3)
+        self._packed = None
+
+    _dtype = ContextParallelDecoder3D._dtype
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _pack(self):
+        dt, dev = self._dtype(), self.conv_in.conv.weight.device
+
+        def h(t):
+            return t.detach().to(device=dev, dtype=dt).contiguous()
+
+        def w27(c, pad_in=None):
+            w = c.conv.weight.detach().float().permute(0, 2, 3, 4, 1)
+            if pad_in:
+                w = torch.nn.functional.pad(w, (0, pad_in - w.shape[-1]))
+            return h(w), h(c.conv.bias)
+
+        def res(r):
+            p = {"n1": (h(r.norm1.weight), h(r.norm1.bias)), "c1": w27(r.conv1), "n2": (h(r.norm2.weight), h(r.norm2.bias)),
+                 "c2": w27(r.conv2)}
+            if hasattr(r, "nin_shortcut"):
+                p["nin"] = (h(r.nin_shortcut.weight.detach()[:, :, 0, 0, 0]), h(r.nin_shortcut.bias))
+            return p
+
+        pk = {"in": w27(self.conv_in, ZQ_PAD), "down": [], "mid": [res(self.mid.block_1), res(self.mid.block_2)],
+              "nout": (h(self.norm_out.weight), h(self.norm_out.bias)), "out": w27(self.conv_out)}
+        for lvl in self.down:
+            e = {"res": [res(r) for r in lvl.block]}
+            if hasattr(lvl, "downsample"):
+                e["down"] = (h(lvl.downsample.conv.weight.detach().permute(0, 2, 3, 1)), h(lvl.downsample.conv.bias),
+                             lvl.downsample.compress_time)
+            pk["down"].append(e)
+        self._packed = pk
+        return pk
+
+    @staticmethod
+    def _causal(buf, wb, T, H, W, residual=None, out=None):
+        HW = H * W
+        buf[:HW].copy_(buf[2 * HW:3 * HW])                           # the first frame twice in front (cp_enc_dec.py:268)
+        buf[HW:2 * HW].copy_(buf[2 * HW:3 * HW])
+        return ops.conv3d_causal(buf, wb[0], T, H, W, wb[1], residual=residual, out=out)
+
+    def _res(self, p, x, T, H, W):
+        HW, Cin, Cout = H * W, x.shape[1], p["c1"][0].shape[0]
+        buf = torch.empty(((T + 2) * HW, Cin), dtype=x.dtype, device=x.device)
+        ops.groupnorm(x, p["n1"][0], p["n1"][1], 1, 1e-6, True, out=buf[2 * HW:])
+        h = self._causal(buf, p["c1"], T, H, W)
+        buf = buf if Cin == Cout else torch.empty(((T + 2) * HW, Cout), dtype=x.dtype, device=x.device)
+        ops.groupnorm(h, p["n2"][0], p["n2"][1], 1, 1e-6, True, out=buf[2 * HW:])
+        skip = ops.linear(x, p["nin"][0], p["nin"][1]) if "nin" in p else x
+        return self._causal(buf, p["c2"], T, H, W, residual=skip, out=h)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x (1, 3, T, H, W) in [-1, 1] -> moments (1, 2 z_channels, (T - 1) / 4 + 1, H / 8, W / 8) in the model's dtype"""
+        pk = self._packed or self._pack()
+        dt = self._dtype()
+        B, Cx, T, H, W = x.shape
+        assert B == 1 and Cx == self.in_channels and H % 8 == 0 and W % 8 == 0
+        buf = torch.zeros(((T + 2) * H * W, ZQ_PAD), dtype=dt, device=x.device)
+        buf[2 * H * W:, :Cx] = x[0].permute(1, 2, 3, 0).reshape(-1, Cx).to(dt)
+        h = self._causal(buf, pk["in"], T, H, W)
+        del buf
+        for e in pk["down"]:
+            for p in e["res"]:
+                h = self._res(p, h, T, H, W)
+            if "down" in e:
+                w9, bias, compress_time = e["down"]
+                if compress_time and T > 1:
+                    h = ops.time_avgpool2(h, T, H * W)
+                    T = (T + 1) // 2 if T % 2 else T // 2
+                h, H, W = ops.conv2d_3x3_s2p(h.view(T, H, W, h.shape[1]), w9, bias, pad=(0, 1, 0, 1))
+        for p in pk["mid"]:
+            h = self._res(p, h, T, H, W)
+        C = h.shape[1]
+        buf = torch.empty(((T + 2) * H * W, C), dtype=dt, device=x.device)
+        ops.groupnorm(h, pk["nout"][0], pk["nout"][1], 1, 1e-6, True, out=buf[2 * H * W:])
+        m = self._causal(buf, pk["out"], T, H, W)
+        return ops.tokens_to_nchw5(m, 1, 2 * self.z_channels, T, H, W)
+
+    @torch.no_grad()
+    def encode(self, x, sample=True):
+        """``VideoAutoencodingEngine.encode`` (autoencoder.py:218-230): encoder + DiagonalGaussianRegularizer -> z (1, 16, Tl, h, w)"""
+        mean, logvar = torch.chunk(self.forward(x), 2, dim=1)
+        if not sample:
+            return mean
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        return (mean.float() + std.float() * torch.randn_like(mean, dtype=torch.float32)).to(mean.dtype)      # noise drawn in fp32

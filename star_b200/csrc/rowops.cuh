@@ -789,6 +789,28 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
         reinterpret_cast<uint4*>(out)[i] = pack8(f);
     }
 }
+// temporal half of DownSample3D of the CogVideoX 3-D VAE encoder (cp_enc_dec.py:581-596): avg_pool1d(k = 2, s = 2) over the frames
+// of a [(T HW), C] clip; for odd T the first frame is kept and the remaining T - 1 are pooled.  per8 = HW * C / 8.
+__global__ void time_avgpool2_kernel(const __half* __restrict__ x, __half* __restrict__ out, int T, long long per8) {
+    const int odd = T & 1;
+    const int To = odd ? (T + 1) / 2 : T / 2;
+    const long long n = (long long)To * per8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int to = (int)(i / per8);
+        const long long off = i - (long long)to * per8;
+        if (odd && to == 0) {
+            reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(x) + off);
+            continue;
+        }
+        const long long t0 = odd ? 2 * to - 1 : 2 * to;
+        float f[8], g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t0 * per8 + off), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + (t0 + 1) * per8 + off), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.5f * (f[j] + g[j]);
+        reinterpret_cast<uint4*>(out)[i] = pack8(f);
+    }
+}
 // nearest x2 upsample then drop the first and last row (unet_v2v.py:563-564): out H' = 2H-2, W' = 2W
 // crop = 0: plain nearest x2 (the VAE decoder's Upsample2D), out H' = 2H
 __global__ void upsample2x_crop_kernel(const __half* __restrict__ x, __half* __restrict__ out, int BT, int H, int W,

@@ -779,6 +779,16 @@ int star_add(const void* a, const void* b, void* out, long long n, void* stream)
     return 0;
 }
 
+int star_time_avgpool2(const void* X, void* out, int T, long long HW, int C, void* stream) {
+    if (C % 8) return fail("star_time_avgpool2: C must be a multiple of 8");
+    if (T < 2) return fail("star_time_avgpool2: needs at least two frames");
+    const long long per8 = HW * C / 8;
+    const int To = (T & 1) ? (T + 1) / 2 : T / 2;
+    time_avgpool2_kernel<<<grid_for(per8 * To, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, (__half*)out, T, per8);
+    STAR_LAUNCH_CHECK("time_avgpool2");
+    return 0;
+}
+
 int star_upsample2x(const void* X, void* out, int BT, int H, int W, int C, int crop_rows, void* stream) {
     if (C % 8) return fail("star_upsample2x: C must be a multiple of 8");
     if (crop_rows != 0 && crop_rows != 1) return fail("star_upsample2x: crop_rows must be 0 or 1");

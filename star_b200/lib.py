@@ -40,6 +40,7 @@ SIGNATURES = {
     "star_liem_spatial_gate": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "star_concat_add": (_i, [_p, _i, _p, _p, _i, _p, _ll, _p]),
     "star_add": (_i, [_p, _p, _p, _ll, _p]),
+    "star_time_avgpool2": (_i, [_p, _p, _i, _ll, _i, _p]),
     "star_upsample2x_crop": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "star_upsample2x": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "star_softmax_rows": (_i, [_p, _ll, _ll, _i, _p]),

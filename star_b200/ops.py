@@ -357,6 +357,19 @@ def add(a, b):
 
 
 @_traced
+def time_avgpool2(x, T, HW):
+    """frame-pair average of a [(T HW), C] clip (odd T: first frame kept): -> [(ceil(T/2) HW), C]"""
+    _dev(x)
+    C = x.shape[1]
+    assert x.is_contiguous() and x.shape[0] == T * HW
+    To = (T + 1) // 2 if T % 2 else T // 2
+    out = torch.empty((To * HW, C), dtype=_dt(), device=x.device)
+    L = _lib()
+    _L.check(L.star_time_avgpool2(_p(x), _p(out), T, HW, C, _st()), "star_time_avgpool2")
+    return out
+
+
+@_traced
 def upsample2x_crop(x, BT, H, W):
     _dev(x)
     C = x.shape[1]

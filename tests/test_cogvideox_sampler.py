@@ -68,19 +68,27 @@ def test_sampler_matches_reference(steps):
 
 def _pipeline_pair(dit_kw, vae_kw, dtype, device):
     from tests.test_cogvideox import _dit_pair
-    from tests.test_cogvideox_vae import _pair
+    from tests.test_cogvideox_vae import _enc_pair, _pair
     ref_dit, net, _x, _t, ctx = _dit_pair(dit_kw, dtype, device)
     ref_dec, dec, _ = _pair(vae_kw, device=device, dtype=dtype)
-    return ref_dit, net, ref_dec, dec, ctx
+    ref_enc, enc, _ = _enc_pair(vae_kw, device=device, dtype=dtype)
+    return ref_dit, net, (ref_enc, ref_dec), (enc, dec), ctx
 
 
-def _reference_pipeline(ref_dit, ref_dec, cond, uc, lq_latent, steps, seed, scale_factor=0.7):
-    """sample_sr.py:186-230 on the reference's own modules (DiT behind the sat shim, sampler stack, 3-D VAE decoder)"""
+def _reference_pipeline(ref_dit, ref_vae, cond, uc, lq, steps, seed, scale_factor=0.7):
+    """sample_sr.py:186-230 / diffusion_video.py:245-292 on the reference's own modules (3-D VAE encoder + Gaussian posterior sample,
+    DiT behind the sat shim, sampler stack, 3-D VAE decoder); lq (1, F, 3, H, W)"""
     from oracle.cogvideox_sampler import build_reference_sampler, reference_sample
-    from oracle.cogvideox_vae import reference_decode_latent
-    sampler, den = build_reference_sampler(num_steps=steps, device=str(lq_latent.device))
+    from oracle.cogvideox_vae import load_reference_vae, reference_decode_latent, reference_encode_moments
+    ref_enc, ref_dec = ref_vae
+    sampler, den = build_reference_sampler(num_steps=steps, device=str(lq.device))
     torch.manual_seed(seed)
-    randn = torch.randn(lq_latent.shape, dtype=torch.float32).to(lq_latent.device)
+    F, H, W = lq.shape[1], lq.shape[3], lq.shape[4]
+    randn = torch.randn((1, (F - 1) // 4 + 1, 16, H // 8, W // 8), dtype=torch.float32).to(lq.device)
+    moments = reference_encode_moments(ref_enc, lq.permute(0, 2, 1, 3, 4).contiguous())
+    mean, logvar = torch.chunk(moments, 2, dim=1)                         # DiagonalGaussianDistribution.sample (regularizers.py:10-29)
+    zq = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * torch.randn_like(mean)
+    lq_latent = (scale_factor * zq).permute(0, 2, 1, 3, 4).contiguous()
     z = reference_sample(ref_dit, sampler, den, randn, dict(cond), dict(uc), lq_latent)
     latent = (1.0 / scale_factor) * z.permute(0, 2, 1, 3, 4).contiguous()
     frames = reference_decode_latent(ref_dec, latent).float().permute(0, 2, 1, 3, 4)
@@ -89,7 +97,8 @@ def _reference_pipeline(ref_dit, ref_dec, cond, uc, lq_latent, steps, seed, scal
 
 @pytest.mark.reference
 def test_cogvideox_pipeline_host_graph_on_emulated_kernels(monkeypatch):
-    """latents -> frames through DiT + sampler + 3-D VAE (reduced sizes, 4 steps) against the same chain of reference modules"""
+    """LQ frames -> frames through 3-D VAE encode + DiT + sampler + 3-D VAE decode (reduced sizes, 4 steps) against the same chain of
+    reference modules"""
     from oracle import kernel_ref as KR
     from star_b200 import ops
     from star_b200.cogvideox import sample_sr
@@ -98,11 +107,11 @@ def test_cogvideox_pipeline_host_graph_on_emulated_kernels(monkeypatch):
     for name in dir(KR):
         if not name.startswith("_") and callable(getattr(KR, name)) and hasattr(ops, name):
             monkeypatch.setattr(ops, name, getattr(KR, name))
-    ref_dit, net, ref_dec, dec, ctx = _pipeline_pair(SMALL_DIT, SMALL, torch.float16, "cpu")
+    ref_dit, net, ref_vae, (enc, dec), ctx = _pipeline_pair(SMALL_DIT, SMALL, torch.float16, "cpu")
     cond, uc = {"crossattn": ctx[:1]}, {"crossattn": torch.zeros_like(ctx[:1])}
-    lq = 0.7 * torch.randn(1, 3, 16, 8, 12, generator=torch.Generator().manual_seed(9))
-    want, z_ref = _reference_pipeline(ref_dit, ref_dec, cond, uc, lq, steps=4, seed=77)
-    got, z = sample_sr(net, dec, cond, uc, lq, num_steps=4, seed=77)
+    lq = torch.rand(1, 9, 3, 64, 96, generator=torch.Generator().manual_seed(9)) * 2 - 1          # LQ clip, already upsampled
+    want, z_ref = _reference_pipeline(ref_dit, ref_vae, cond, uc, lq, steps=4, seed=77)
+    got, z = sample_sr(net, dec, cond, uc, lq=lq, encoder=enc, num_steps=4, seed=77)
     assert got.shape == want.shape == (1, 9, 3, 64, 96)
     assert rel_l2(z, z_ref) < 1e-2 and rel_l2(got, want) < 1e-2
 
@@ -118,11 +127,11 @@ def test_cogvideox_pipeline_gpu():
         pytest.skip("reference files not staged")
     kw = dict(num_layers=2, hidden_size=3072, num_attention_heads=48, num_frames=17, latent_height=16, latent_width=24,
               text_length=226, text_hidden_size=4096, lora_r=64, time_embed_dim=512)
-    ref_dit, net, ref_dec, dec, ctx = _pipeline_pair(kw, {}, torch.float16, "cuda")
+    ref_dit, net, ref_vae, (enc, dec), ctx = _pipeline_pair(kw, {}, torch.float16, "cuda")
     cond, uc = {"crossattn": ctx[:1]}, {"crossattn": torch.zeros_like(ctx[:1])}
-    lq = (0.7 * torch.randn(1, 5, 16, 16, 24, generator=torch.Generator().manual_seed(9))).cuda()
-    want, z_ref = _reference_pipeline(ref_dit, ref_dec, cond, uc, lq, steps=6, seed=5)
-    got, z = sample_sr(net, dec, cond, uc, lq, num_steps=6, seed=5)
+    lq = (torch.rand(1, 17, 3, 128, 192, generator=torch.Generator().manual_seed(9)) * 2 - 1).cuda()
+    want, z_ref = _reference_pipeline(ref_dit, ref_vae, cond, uc, lq, steps=6, seed=5)
+    got, z = sample_sr(net, dec, cond, uc, lq=lq, encoder=enc, num_steps=6, seed=5)
     e_z, e_x = rel_l2(z, z_ref), rel_l2(got, want)
     print(f"[cogvideox pipeline fp16, 6 steps] latent rel-L2 {e_z:.2e}, frames rel-L2 {e_x:.2e}")
     assert got.shape == want.shape == (1, 17, 3, 128, 192) and torch.isfinite(got).all()

@@ -23,6 +23,18 @@ def _pair(kw, seed=3, device="cpu", dtype=torch.float16):
     return ref.to(device), mine.to(device=device, dtype=dtype).eval(), sd
 
 
+def _enc_pair(kw, seed=6, device="cpu", dtype=torch.float16):
+    from oracle.cogvideox_vae import build_reference_encoder
+    from star_b200.cogvideox.vae3d import ContextParallelEncoder3D
+    from star_b200.utils.synth import synth_state_dict
+    ref = build_reference_encoder(**kw)
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in ref.state_dict().items()}, seed=seed)
+    ref.load_state_dict(sd)
+    mine = ContextParallelEncoder3D(**kw)
+    mine.load_state_dict(sd)
+    return ref.to(device), mine.to(device=device, dtype=dtype).eval(), sd
+
+
 def _patch(monkeypatch):
     from oracle import kernel_ref as KR
     from star_b200 import ops
@@ -62,6 +74,31 @@ def test_decoder_host_graph_on_emulated_kernels(monkeypatch):
         alone = ref(z[:, :, 3:5].contiguous(), clear_fake_cp_cache=True)
     assert rel_l2(mine(z[:, :, 3:5].contiguous()), alone) < 3e-3
     assert rel_l2(got[:, :, 9:17], alone) > 1e-2                              # ... and that differs from the chunked result
+
+
+@pytest.mark.reference
+def test_encoder_host_graph_on_emulated_kernels(monkeypatch):
+    """9 frames of 32x48 -> moments (1, 32, 3, 4, 6): odd clip lengths through both time-compressing DownSample3D levels
+    (9 -> 5 -> 3), the (0,1,0,1)-padded stride-2 convs, clip-wide GroupNorm, first-frame replication of the causal convs"""
+    from oracle.cogvideox_vae import build_reference_encoder, reference_encode_moments
+    from star_b200.cogvideox.vae3d import ContextParallelEncoder3D
+    _patch(monkeypatch)
+    with torch.device("meta"):
+        assert {k: tuple(v.shape) for k, v in ContextParallelEncoder3D().state_dict().items()} == \
+               {k: tuple(v.shape) for k, v in build_reference_encoder().state_dict().items()}
+    ref, mine, _ = _enc_pair(SMALL)
+    x = torch.rand(1, 3, 9, 32, 48, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    want = reference_encode_moments(ref, x)
+    got = mine(x)
+    assert got.shape == want.shape == (1, 32, 3, 4, 6)
+    assert rel_l2(got, want) < 3e-3
+    even = torch.rand(1, 3, 8, 16, 16, generator=torch.Generator().manual_seed(4)) * 2 - 1      # even T: plain pair pooling
+    assert rel_l2(mine(even), reference_encode_moments(ref, even)) < 3e-3
+    torch.manual_seed(0)
+    z = mine.encode(x)
+    torch.manual_seed(0)
+    mean, logvar = got.float().chunk(2, dim=1)
+    assert torch.allclose(z.float(), mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * torch.randn_like(got[:, :16], dtype=torch.float32), atol=1e-2)
 
 
 def test_spatial_norm_index_rule():
@@ -140,4 +177,31 @@ def test_decoder_vs_reference_gpu(dtype, tol):
     err_ref = rel_l2(ref16, want)
     print(f"[cogvideox vae {dtype}] star {err:.2e}  reference-in-{dtype} {err_ref:.2e}")
     assert torch.isfinite(got.float()).all()
+    assert err < tol and err < 1.5 * err_ref + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,HW,C", [(9, 640, 128), (8, 1000, 256), (2, 77, 64), (49, 120, 128)])
+def test_time_avgpool2(env, T, HW, C):
+    ops, KR = env
+    x = torch.randn(T * HW, C, device="cuda", generator=torch.Generator(device="cuda").manual_seed(T)).half()
+    got, want = ops.time_avgpool2(x, T, HW), KR.time_avgpool2(x, T, HW)
+    assert got.shape == want.shape and torch.equal(got, want)                  # one rounding of an exact fp32 sum
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 1.6e-2)])
+def test_encoder_vs_reference_gpu(dtype, tol):
+    """full-width encoder (ch 128, 3 res blocks per level), 17 frames of 96x128 -> moments (1, 32, 5, 12, 16)"""
+    from oracle.cogvideox_vae import reference_encode_moments, vae_reference_available
+    if not vae_reference_available():
+        pytest.skip("reference VAE file not staged (oracle/_ref)")
+    ref, mine, _ = _enc_pair({}, device="cuda", dtype=dtype)
+    x = (torch.rand(1, 3, 17, 96, 128, generator=torch.Generator().manual_seed(2)) * 2 - 1).cuda()
+    want = reference_encode_moments(ref, x)
+    got = mine(x.to(dtype))
+    err = rel_l2(got, want)
+    err_ref = rel_l2(reference_encode_moments(ref.to(dtype), x.to(dtype)), want)
+    print(f"[cogvideox vae encoder {dtype}] star {err:.2e}  reference-in-{dtype} {err_ref:.2e}")
+    assert got.shape == want.shape == (1, 32, 5, 12, 16) and torch.isfinite(got.float()).all()
     assert err < tol and err < 1.5 * err_ref + 1e-3

@@ -49,6 +49,49 @@ def main():
     print("  ops:", ", ".join(f"{k} {v:.2f} ms ({100 * v / tot:.0f}%)" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])))
 
 
+def vae3d_encode_leg(dev, dtype, F, H, W):
+    """the encode in front of config 4 (diffusion_video.py:279-282): the pre-upsampled LQ clip (49 x 480 x 720) -> latent"""
+    from star_b200.cogvideox.vae3d import ContextParallelEncoder3D
+    from star_b200.utils.synth import synth_tensor
+    try:
+        with torch.device("meta"):
+            enc = ContextParallelEncoder3D()
+        sd = {k: synth_tensor(k, v.shape, 13, dev) for k, v in enc.state_dict().items()}
+        enc.load_state_dict(sd, assign=True)
+        enc = enc.to(dtype).eval()
+        x = (torch.rand(1, 3, F, H, W, generator=torch.Generator().manual_seed(6)) * 2 - 1).to(dev, dtype)
+        m = enc(x)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        m = enc(x)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        leg = {"frames": F, "encode_ms_per_clip": ms, "encode_ms_per_frame": ms / F, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+               "finite": bool(torch.isfinite(m.float()).all())}
+        try:
+            from oracle.cogvideox_vae import build_reference_encoder, reference_encode_moments, vae_reference_available
+            if vae_reference_available():
+                renc = build_reference_encoder({k: v.float() for k, v in sd.items()}).to(dev, dtype)
+                del sd
+                reference_encode_moments(renc, x)
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                rm = reference_encode_moments(renc, x)
+                r1.record()
+                torch.cuda.synchronize()
+                leg["gpu_reference"] = {"encode_ms_per_clip": r0.elapsed_time(r1), "star_over_reference": r0.elapsed_time(r1) / ms,
+                                        "rel_l2_star_vs_reference_same_dtype": ((m.float() - rm.float()).norm() / rm.float().norm()).item()}
+        except Exception as e:
+            leg["gpu_reference"] = {"unavailable": repr(e)[:200]}
+        return leg
+    except Exception as e:                                                # a leg must never break the bench line
+        return {"unavailable": repr(e)[:300]}
+
+
 def vae3d_leg(dev, dtype, T, H, W, step_ms):
     """the decode tail of config 4 (sample_sr.py:206-230): 13 latent frames of 60x90 -> 49 frames of 480x720 through the 3-D
     causal VAE decoder in the reference's chunk protocol (3 + 5 x 2 latent frames), causal-conv context kept on the GPU"""
@@ -111,20 +154,25 @@ def vae3d_leg(dev, dtype, T, H, W, step_ms):
             gpu_ref = {"unavailable": "oracle/_ref not staged on this box"}
     except Exception as e:                                                # the baseline must never break the bench line
         gpu_ref = {"unavailable": repr(e)[:200]}
+    del frames
+    torch.cuda.empty_cache()
+    enc_leg = vae3d_encode_leg(dev, dtype, (T - 1) * 4 + 1, 8 * H, 8 * W)
     return {"what": "CogVideoX 3-D causal VAE decode of the clip (SURVEY 8 f4), reference chunk protocol, context frames on the GPU",
+            "encode": enc_leg,
             "gpu_reference": gpu_ref,
             "frames": int(nf), "decode_ms_per_clip": ms, "decode_ms_per_frame": ms / nf, "decode_tflops_per_s": flops / ms / 1e9,
             "algorithmic_tflop_per_clip": flops / 1e12, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
             "launches_per_clip": int((ops.launch_count() - n0) // 2), "finite": bool(torch.isfinite(frames.float()).all()),
             "frames_per_s_denoise_plus_decode": nf / ((50 * step_ms + ms) / 1e3),
+            "frames_per_s_encode_denoise_decode": (nf / ((50 * step_ms + ms + enc_leg["encode_ms_per_clip"]) / 1e3)) if enc_leg.get("encode_ms_per_clip") else None,
             "parity": "tests/test_cogvideox_vae.py (reference's unmodified cp_enc_dec.py)"}
 
 
 def run_config4(args):
     """bench.py --workload cogvideox: BASELINE config 4 -- CogVideoX-5B heavy-deg 4x, 49 frames 720x480 (latent 13 x 60 x 90,
     patch 2 -> 17 550 image + 226 text tokens), the whole 42-layer DiffusionTransformer with LoRA r = 512 merged, bf16 (the
-    reference's dtype), CFG pair as batch 2.  A "step" = one DiT forward of the CFG pair + guidance combine (the sampler's
-    elementwise update acts on a 1.4 MB latent)."""
+    reference's dtype), CFG pair as batch 2.  A "step" = one step of the shipped sampler (star_b200/cogvideox/sampling.py:
+    DiT forward of the CFG pair, VideoScaling, DynamicCFG, DPM-Solver++(2M) SDE update)."""
     import json
     import torch.distributed as dist
     from bench import ClockSampler, measured_peaks
@@ -152,33 +200,40 @@ def run_config4(args):
         p.data = torch.empty(0, device=dev)
     torch.cuda.empty_cache()
     T, H, W, tl = 13, 60, 90, 226
+    from star_b200.cogvideox.sampling import VPSDEDPMPP2MSampler
+    sampler = VPSDEDPMPP2MSampler(num_steps=50, dtype=dtype)      # the shipped schedule / DynamicCFG / VideoScaling (yaml :20-33,:157-174)
+    st_mid = sampler.plan.steps[25]                              # a mid-schedule step: two noise draws, 2M history term
+    torch.manual_seed(0)                                         # same solver noise on every rank
     g = torch.Generator().manual_seed(0)
     # CFG: split the pair across 2 ranks when available (the only parallel axis of one clip); else batch 2
     split = world >= 2
     bsz = 1 if split else 2
-    x = torch.randn(2, T, 32, H, W, generator=g)
-    ctx = torch.randn(2, tl, 4096, generator=g)
-    x_pin, ctx_pin = x.pin_memory(), ctx.pin_memory()
+    x = torch.randn(1, T, 16, H, W, generator=g)                 # noisy latent (fp32, sampler state)
+    lq1 = torch.randn(1, T, 16, H, W, generator=g)               # VAE-encoded LQ clip
+    ctx = torch.randn(2, tl, 4096, generator=g)                  # [uncond, cond] T5 embeddings
+    x_pin, lq_pin, ctx_pin = x.pin_memory(), lq1.pin_memory(), ctx.pin_memory()
     lo = (rank % 2) if split else 0
-    xd, cd = x[lo:lo + bsz].to(dev), ctx[lo:lo + bsz].to(dev)
-    ts = torch.full((bsz,), 500, device=dev)
+    xd, lqd, cd = x.to(dev), torch.cat((lq1, lq1), 0).to(dev), ctx.to(dev, dtype)
+    old = torch.randn(1, T, 16, H, W, generator=g).to(dev)       # previous step's denoised latent
 
-    def step(xx, cc):
-        out = net(xx, timesteps=ts, context=cc).float()
-        if split:
-            both = [torch.empty_like(out) for _ in range(world)]
-            dist.all_gather(both, out)
-            cond, unc = both[0], both[1]
-        else:
-            cond, unc = out[:1], out[1:]
-        return unc + 6.0 * (cond - unc)                         # DynamicCFG at its plateau (guiders.py:61-79)
+    def net_pair(xin, timesteps=None, context=None):
+        """the CFG pair: one batch-2 forward, or one branch per rank + one all-gather of the 1.4 MB prediction"""
+        if not split:
+            return net(xin, timesteps=timesteps, context=context)
+        out = net(xin[lo:lo + 1], timesteps=timesteps[lo:lo + 1], context=context[lo:lo + 1]).contiguous()
+        both = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(both, out)
+        return torch.cat(both[:2], 0)
+
+    def step(xx, lq2, cc):
+        return sampler.step(net_pair, xx, old, st_mid, cc, lq2)[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
     for _ in range(max(args.warmup, 1)):
-        step(xd, cd)
+        step(xd, lqd, cd)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -187,7 +242,7 @@ def run_config4(args):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        out = step(xd, cd)
+        out = step(xd, lqd, cd)
     b.record()
     barrier()
     launches = ops.launch_count() - n0
@@ -195,7 +250,8 @@ def run_config4(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res = step(x_pin[lo:lo + bsz].to(dev, non_blocking=True), ctx_pin[lo:lo + bsz].to(dev, non_blocking=True)).cpu()
+        lq_d = lq_pin.to(dev, non_blocking=True)
+        res = step(x_pin.to(dev, non_blocking=True), torch.cat((lq_d, lq_d), 0), ctx_pin.to(dev, non_blocking=True).to(dtype)).cpu()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
@@ -204,7 +260,7 @@ def run_config4(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = tt.tolist()
     ops.trace_begin()
-    step(xd, cd)
+    step(xd, lqd, cd)
     trace = ops.trace_end()
     att = [t_ms for name, sig, t_ms in trace if name == "attention"]
     per_op = {}
@@ -228,12 +284,12 @@ def run_config4(args):
                            "model": f"DiffusionTransformer {layers} layers x 3072, 48 heads, LoRA r=512 merged, synthetic weights"
                                     + (" (REDUCED DEPTH, debug)" if args.small else ""),
                            "parallelism": "CFG pair split over 2 ranks, one all-gather of the 1.4 MB prediction per step" if split else "single GPU, CFG pair as batch 2",
-                           "step": "one DiT forward of the CFG pair + guidance combine",
+                           "step": "one VPSDEDPMPP2MSampler step (index 25 of 50): DiT forward of the CFG pair on cat(noisy, LQ) latents, VideoScaling, DynamicCFG, DPM-Solver++(2M) SDE update with its two noise draws",
                            "l2": "activations (109 MB per 3072-wide token matrix per sample) exceed the L2 across a layer; no explicit flush"},
                 "clocks": clocks.stop(), "gpu_launches": int(launches),
                 "e2e": {"value": 49.0 / (50 * e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int((x[0].numel() + ctx[0].numel()) * 4 * bsz), "d2h_bytes_per_step": int(res.numel() * 4),
-                        "api": "DiffusionTransformer.forward(host tensors) + CFG combine, .cpu() per step"},
+                        "h2d_bytes_per_step": int((x.numel() + lq1.numel() + ctx.numel()) * 4), "d2h_bytes_per_step": int(res.numel() * 4),
+                        "api": "VPSDEDPMPP2MSampler.step(host latent, LQ latent, text embeddings) -> next latent .cpu()"},
                 "roofline": {"kernel": "attn4_fwd_kernel (3-D full attention, 48 heads, N = 17 776)", "bound": "tensor",
                              "achieved": aflops / (sum(att) / max(len(att), 1) * 1e-3) / 1e12 if att else None, "peak": peaks["tflops"],
                              "unit": "TFLOP/s", "frac": (aflops / (sum(att) / max(len(att), 1) * 1e-3) / 1e12 / peaks["tflops"]) if att else None,
