@@ -4,8 +4,8 @@ cogvideox-based/sat/vae_modules/cp_enc_dec.py (ContextParallelDecoder3D and ever
 reference tree (/root/reference, or the staged git-ignored copy oracle/_ref written by oracle/stage_reference.py).  Its three
 foreign imports are shimmed with what they are at context-parallel size 1 (yaml :103 `cp_size: 1`):
     sgm.util.get_context_parallel_{group,rank,world_size,group_rank}  -> None, 0, 1, 0
-    vae_modules.utils.SafeConv3d                                     -> torch.nn.Conv3d (the reference's subclass only splits
-                                                                        inputs above 2 GB along T with the exact overlap, utils.py:72-91)
+    vae_modules.utils.SafeConv3d                                     -> restated (Conv3d that splits inputs above 2 GB along T with the
+                                                                        exact overlap, utils.py:72-91; its module imports fsspec / PIL)
     torch.distributed.get_rank() / get_world_size()                  -> 0 / 1 while the decoder runs (no process group in a test)
 PINNING STATUS: the decoder arithmetic of SURVEY row f4 is pinned to the reference's own file through this module.
 Never imported by the product.
@@ -53,7 +53,18 @@ def load_reference_vae():
     u.get_context_parallel_group_rank = lambda: 0
 
     class SafeConv3d(torch.nn.Conv3d):
-        pass
+        """restated from vae_modules/utils.py:72-91 (that file imports fsspec / PIL / safetensors and cannot be loaded here):
+        inputs above 2 GB are convolved in chunks along T, each chunk prefixed with the kernel_size - 1 frames before it"""
+
+        def forward(self, input):
+            gb = torch.prod(torch.tensor(input.shape)).item() * 2 / 1024 ** 3
+            if gb <= 2:
+                return super().forward(input)
+            k = self.kernel_size[0]
+            chunks = torch.chunk(input, int(gb / 2) + 1, dim=2)
+            if k > 1:
+                chunks = [chunks[0]] + [torch.cat((chunks[i - 1][:, :, -k + 1:], chunks[i]), dim=2) for i in range(1, len(chunks))]
+            return torch.cat([super(SafeConv3d, self).forward(c) for c in chunks], dim=2)
     _mod("vae_modules.utils").SafeConv3d = SafeConv3d
     spec = importlib.util.spec_from_file_location("vae_modules.cp_enc_dec", path)
     m = importlib.util.module_from_spec(spec)

@@ -154,6 +154,9 @@ def vae3d_leg(dev, dtype, T, H, W, step_ms):
             gpu_ref = {"unavailable": "oracle/_ref not staged on this box"}
     except Exception as e:                                                # the baseline must never break the bench line
         gpu_ref = {"unavailable": repr(e)[:200]}
+    finite = bool(torch.isfinite(frames.float()).all())
+    launches_per_clip = int((ops.launch_count() - n0) // 2)
+    peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     del frames
     torch.cuda.empty_cache()
     enc_leg = vae3d_encode_leg(dev, dtype, (T - 1) * 4 + 1, 8 * H, 8 * W)
@@ -161,8 +164,8 @@ def vae3d_leg(dev, dtype, T, H, W, step_ms):
             "encode": enc_leg,
             "gpu_reference": gpu_ref,
             "frames": int(nf), "decode_ms_per_clip": ms, "decode_ms_per_frame": ms / nf, "decode_tflops_per_s": flops / ms / 1e9,
-            "algorithmic_tflop_per_clip": flops / 1e12, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-            "launches_per_clip": int((ops.launch_count() - n0) // 2), "finite": bool(torch.isfinite(frames.float()).all()),
+            "algorithmic_tflop_per_clip": flops / 1e12, "peak_mem_gb": peak_gb,
+            "launches_per_clip": launches_per_clip, "finite": finite,
             "frames_per_s_denoise_plus_decode": nf / ((50 * step_ms + ms) / 1e3),
             "frames_per_s_encode_denoise_decode": (nf / ((50 * step_ms + ms + enc_leg["encode_ms_per_clip"]) / 1e3)) if enc_leg.get("encode_ms_per_clip") else None,
             "parity": "tests/test_cogvideox_vae.py (reference's unmodified cp_enc_dec.py)"}
