@@ -4,5 +4,5 @@ DiscreteDenoiser / VideoScaling), the 3-D causal VAE (encoder and decoder), and 
 from .dit_block import DiTLayer  # noqa: F401
 from .model import DiffusionTransformer, dit_manifest, rope_tables  # noqa: F401
 from .pipeline import sample_sr  # noqa: F401
-from .sampling import StepPlan, VPSDEDPMPP2MSampler, sample_sr_latent  # noqa: F401
+from .sampling import StepPlan, VPSDEDPMPP2MSampler, sample_sr_latent, split_cfg_pair  # noqa: F401
 from .vae3d import ContextParallelDecoder3D, ContextParallelEncoder3D  # noqa: F401

@@ -129,6 +129,24 @@ class VPSDEDPMPP2MSampler:
         return x
 
 
+def split_cfg_pair(network, group=None):
+    """Multi-GPU axis of one CogVideoX clip: the two branches of the CFG pair on two ranks.  Wraps ``network`` so that
+    rank 0 / 1 of ``group`` evaluates row 0 (unconditional) / row 1 (conditional) of the batch-2 input the sampler builds, and ONE
+    all-gather of the (1, T, 16, h, w) prediction per solver step reassembles the pair -- every rank then applies the identical
+    guidance and solver update (same seed => same solver noise), so the ranks stay bit-identical without further traffic."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    assert world == 2, "the CFG pair splits over exactly two ranks (more GPUs = replicas of other clips)"
+
+    def pair(xin, timesteps=None, context=None, **kw):
+        assert xin.shape[0] == 2, "split_cfg_pair serves one clip (batch 1) per pair of ranks"
+        out = network(xin[rank:rank + 1], timesteps=timesteps[rank:rank + 1], context=context[rank:rank + 1], **kw).contiguous()
+        both = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(both, out, group=group)
+        return torch.cat(both, 0)
+    return pair
+
+
 @torch.no_grad()
 def sample_sr_latent(network, sampler, cond, uc, lq_latent, generator_seed=None, randn=None):
     """the part of ``sample_sr`` (diffusion_video.py:245-292) after the LQ clip has been encoded: start noise of the LQ latent's

@@ -369,6 +369,7 @@ gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __h
 // frame when T is odd (> 1): ts = 0 for t = 0, else 1 + (t-1)(Tl-1)/(T-1); otherwise ts = t*Tl/T.  One sample (B = 1).
 struct GnModGeom {
     int T, H, W, Tl, Hl, Wl, split_first;
+    int hshift, wshift;       // log2(H / Hl), log2(W / Wl) when those ratios are powers of two (the VAE's: 1, 2, 4, 8), else -1
 };
 
 __global__ void __launch_bounds__(GN2_THREADS)
@@ -391,29 +392,60 @@ gn_apply_mod_kernel(const __half* __restrict__ x, const float* __restrict__ ab, 
             a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
         }
     }
-    const int HW = gm.H * gm.W;
+    const int H = gm.H, W = gm.W, HW = H * W;
+    auto t_src = [&](int t) {
+        if (gm.split_first) return t == 0 ? 0 : 1 + ((t - 1) * (gm.Tl - 1)) / (gm.T - 1);
+        return (t * gm.Tl) / gm.T;
+    };
+    // one division set per slab, then (t, h, w) advance incrementally: the row index arithmetic must not outweigh 48 bytes of traffic
     for (long long g = g0; g < g1; ++g) {
-        const long long r0 = g * GN2_SLAB;
-        const long long r1 = min(rows, r0 + GN2_SLAB);
-        for (long long r = r0 + ln; r < r1; r += lanes) {
-            const int t = (int)(r / HW);
-            const int hw = (int)(r - (long long)t * HW);
-            const int h = hw / gm.W, w = hw - h * gm.W;
-            int ts;
-            if (gm.split_first) ts = t == 0 ? 0 : 1 + (int)(((long long)(t - 1) * (gm.Tl - 1)) / (gm.T - 1));
-            else ts = (int)(((long long)t * gm.Tl) / gm.T);
-            const long long src = ((long long)ts * gm.Hl + (h * gm.Hl) / gm.H) * gm.Wl + (w * gm.Wl) / gm.W;
-            float f[8], fy[8], fb[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + oc * 8)), f);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(ymod + src * ldmod + oc * 8)), fy);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(bmod + src * ldmod + oc * 8)), fb);
+        const int r0 = (int)(g * GN2_SLAB);
+        const int r1 = (int)min(rows, (long long)r0 + GN2_SLAB);
+        int r = r0 + ln;
+        if (r >= r1) continue;
+        int t = r / HW;
+        int h = (r - t * HW) / W;
+        int w = r - t * HW - h * W;
+        int ts = t_src(t);
+        while (r < r1) {
+            uint4 ux[4], uy[4], ub[4];
+            int rr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = fmaf(fmaf(f[j], a[j], b[j]), fy[j], fb[j]);
-                if (silu) y = silu_f(y);
-                f[j] = y;
+            for (int k = 0; k < 4; ++k) {
+                rr[k] = r < r1 ? r : -1;
+                if (rr[k] >= 0) {
+                    const int hs = gm.hshift >= 0 ? (h >> gm.hshift) : (h * gm.Hl) / H;
+                    const int ws = gm.wshift >= 0 ? (w >> gm.wshift) : (w * gm.Wl) / W;
+                    const long long src = ((long long)(ts * gm.Hl + hs) * gm.Wl + ws) * ldmod + oc * 8;
+                    ux[k] = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * C + oc * 8));
+                    uy[k] = __ldg(reinterpret_cast<const uint4*>(ymod + src));
+                    ub[k] = __ldg(reinterpret_cast<const uint4*>(bmod + src));
+                    r += lanes;
+                    w += lanes;
+                    while (w >= W) {
+                        w -= W;
+                        if (++h == H) {
+                            h = 0;
+                            ts = t_src(++t);
+                        }
+                    }
+                }
             }
-            *reinterpret_cast<uint4*>(out + r * C + oc * 8) = pack8(f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (rr[k] < 0) continue;
+                float f[8], fy[8], fb[8];
+                unpack8(ux[k], f);
+                unpack8(uy[k], fy);
+                unpack8(ub[k], fb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y = fmaf(fmaf(f[j], a[j], b[j]), fy[j], fb[j]);
+                    if (silu) y = silu_f(y);
+                    f[j] = y;
+                }
+                *reinterpret_cast<uint4*>(out + (long long)rr[k] * C + oc * 8) = pack8(f);
+            }
         }
     }
 }

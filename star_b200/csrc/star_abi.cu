@@ -687,7 +687,9 @@ int star_groupnorm_mod(const void* X, const void* gamma, const void* beta, const
     STAR_LAUNCH_CHECK("gn_stats2");
     gn_finalize_kernel<<<1, 256, 0, st>>>(stats, (const __half*)gamma, (const __half*)beta, ab, rows, C, eps);
     STAR_LAUNCH_CHECK("gn_finalize");
-    GnModGeom gm{T, H, W, Tl, Hl, Wl, split ? 1 : 0};
+    if (rows > 0x7fffffffll) return fail("star_groupnorm_mod: more than 2^31 rows");
+    auto log2_exact = [](int q) { int s = 0; while ((1 << s) < q) ++s; return (1 << s) == q ? s : -1; };
+    GnModGeom gm{T, H, W, Tl, Hl, Wl, split ? 1 : 0, log2_exact(H / Hl), log2_exact(W / Wl)};
     gn_apply_mod_kernel<<<grid2, GN2_THREADS, 0, st>>>((const __half*)X, ab, (const __half*)Ymod, (const __half*)Bmod,
                                                        ldmod, (__half*)out, rows, C, silu, rg, gm);
     STAR_LAUNCH_CHECK("gn_apply_mod");

@@ -136,3 +136,52 @@ def test_cogvideox_pipeline_gpu():
     print(f"[cogvideox pipeline fp16, 6 steps] latent rel-L2 {e_z:.2e}, frames rel-L2 {e_x:.2e}")
     assert got.shape == want.shape == (1, 17, 3, 128, 192) and torch.isfinite(got).all()
     assert e_z < 2e-2 and e_x < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------- 2 ranks (gloo, CPU)
+def _split_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from star_b200.cogvideox.sampling import VPSDEDPMPP2MSampler, split_cfg_pair
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        lq = torch.randn(1, 3, 16, 6, 8, generator=g)
+        randn = torch.randn(1, 3, 16, 6, 8, generator=g)
+        cond, uc = {"crossattn": torch.randn(1, 226, 32, generator=g)}, {"crossattn": torch.zeros(1, 226, 32)}
+        net = FakeDiT()
+        torch.manual_seed(123)
+        out = VPSDEDPMPP2MSampler(num_steps=6, dtype=torch.float32)(split_cfg_pair(net), randn, cond, uc=uc, lq=torch.cat((lq, lq), 0))
+        q.put((rank, out.numpy(), len(net.calls)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_pair_split_two_ranks_equals_single():
+    """CogVideoX multi-GPU axis: the CFG pair over 2 ranks (one all-gather per step) == the batch-2 run, bit for bit, on both ranks"""
+    import socket
+    import torch.multiprocessing as mp
+    from star_b200.cogvideox.sampling import VPSDEDPMPP2MSampler
+    g = torch.Generator().manual_seed(0)
+    lq = torch.randn(1, 3, 16, 6, 8, generator=g)
+    randn = torch.randn(1, 3, 16, 6, 8, generator=g)
+    cond, uc = {"crossattn": torch.randn(1, 226, 32, generator=g)}, {"crossattn": torch.zeros(1, 226, 32)}
+    torch.manual_seed(123)
+    single = VPSDEDPMPP2MSampler(num_steps=6, dtype=torch.float32)(FakeDiT(), randn, cond, uc=uc, lq=torch.cat((lq, lq), 0))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out, ncalls in res:
+        assert ncalls == 6                                                     # one single-branch forward per step and rank
+        assert torch.equal(torch.from_numpy(out), single)

@@ -148,7 +148,7 @@ def test_conv3d_causal(env, T, H, W, Cin, Cout, res):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("T,Tl,H,W,Hl,Wl,C", [(9, 3, 32, 48, 4, 6, 128), (8, 2, 32, 48, 4, 6, 256), (3, 3, 60, 90, 60, 90, 512),
-                                               (5, 3, 24, 36, 12, 18, 512), (4, 2, 16, 16, 8, 8, 32)])
+                                               (5, 3, 24, 36, 12, 18, 512), (4, 2, 16, 16, 8, 8, 32), (2, 2, 12, 18, 4, 6, 64), (9, 3, 480, 720, 60, 90, 128)])
 def test_groupnorm_mod(env, T, Tl, H, W, Hl, Wl, C):
     ops, KR = env
     g = torch.Generator(device="cuda").manual_seed(T + C)

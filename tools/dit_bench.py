@@ -188,6 +188,8 @@ def run_config4(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if world != 2:
+            raise SystemExit("bench.py --workload cogvideox: one clip splits over exactly 2 GPUs (CFG pair); more GPUs are replicas")
     dtype = torch.bfloat16
     layers = 4 if args.small else 42
     with torch.device("meta"):
@@ -215,18 +217,11 @@ def run_config4(args):
     lq1 = torch.randn(1, T, 16, H, W, generator=g)               # VAE-encoded LQ clip
     ctx = torch.randn(2, tl, 4096, generator=g)                  # [uncond, cond] T5 embeddings
     x_pin, lq_pin, ctx_pin = x.pin_memory(), lq1.pin_memory(), ctx.pin_memory()
-    lo = (rank % 2) if split else 0
     xd, lqd, cd = x.to(dev), torch.cat((lq1, lq1), 0).to(dev), ctx.to(dev, dtype)
     old = torch.randn(1, T, 16, H, W, generator=g).to(dev)       # previous step's denoised latent
 
-    def net_pair(xin, timesteps=None, context=None):
-        """the CFG pair: one batch-2 forward, or one branch per rank + one all-gather of the 1.4 MB prediction"""
-        if not split:
-            return net(xin, timesteps=timesteps, context=context)
-        out = net(xin[lo:lo + 1], timesteps=timesteps[lo:lo + 1], context=context[lo:lo + 1]).contiguous()
-        both = [torch.empty_like(out) for _ in range(world)]
-        dist.all_gather(both, out)
-        return torch.cat(both[:2], 0)
+    from star_b200.cogvideox.sampling import split_cfg_pair
+    net_pair = split_cfg_pair(net) if split else net          # one branch per rank + one all-gather of the 1.4 MB prediction
 
     def step(xx, lq2, cc):
         return sampler.step(net_pair, xx, old, st_mid, cc, lq2)[0]
@@ -272,7 +267,6 @@ def run_config4(args):
     peaks = measured_peaks()
     S = tl + T * (H // 2) * (W // 2)
     aflops = 4.0 * S * S * 64 * 48 * bsz
-    clips = (world // 2) if split else world                   # replicas beyond the CFG pair (different clips in production)
     d, ff = 3072, 4 * 3072
     layer_flops = 2 * (2.0 * S * d * 3 * d + 2.0 * S * d * d + 4.0 * S * d * ff) + 2 * 4.0 * S * S * d   # both CFG branches
     vae_leg = None
