@@ -71,9 +71,10 @@ def _all_gather_varlen(local, counts, dim):
 
 
 class VideoToVideo_sr():
-    def __init__(self, opt, device=torch.device('cuda:0'), text_encoder=None, vae=None, generator=None):
+    def __init__(self, opt, device=torch.device('cuda:0'), text_encoder=None, vae=None, generator=None, cuda_graph=False):
         self.opt = opt
         self.device = device
+        self.cuda_graph = cuda_graph           # serve the denoiser's CFG-pair call from CUDA graphs (launch-bound small latents)
 
         if text_encoder is None:
             from .modules.embedder import FrozenOpenCLIPEmbedder
@@ -91,6 +92,7 @@ class VideoToVideo_sr():
             ret = generator.load_state_dict(load_dict, strict=False)
             logger.info('Load model path {}, with local status {}'.format(cfg.model_path, ret))
         self.generator = generator.half()
+        self._graphed = None
 
         sigmas = noise_schedule(schedule='logsnr_cosine_interp', n=1000, zero_terminal_snr=True,
                                 scale_min=2.0, scale_max=4.0)
@@ -142,8 +144,14 @@ class VideoToVideo_sr():
         chunk_inds = make_chunks(frames_num, interp_f_num=0, max_chunk_len=max_chunk_len) \
             if frames_num > max_chunk_len else None
         extra = {} if noise_sampler is None else {'noise_sampler': noise_sampler}
+        model = self.generator
+        if self.cuda_graph and hasattr(model, "forward_cfg_pair"):
+            if self._graphed is None:
+                from .cuda_graph import GraphedCFGPair
+                self._graphed = GraphedCFGPair(self.generator)
+            model = self._graphed
         return self.diffusion.sample_sr(
-            noise=noised_lr, model=self.generator, model_kwargs=model_kwargs, guide_scale=guide_scale,
+            noise=noised_lr, model=model, model_kwargs=model_kwargs, guide_scale=guide_scale,
             guide_rescale=0.2, solver='dpmpp_2m_sde', solver_mode=solver_mode, return_intermediate=None,
             steps=steps, t_max=total_noise_levels - 1, t_min=0, discretization='trailing',
             chunk_inds=chunk_inds, chunk_parallel=chunk_parallel, **extra)

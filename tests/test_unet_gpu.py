@@ -102,3 +102,38 @@ def test_unet_full_vs_golden():
 def test_smoke_entry():
     from star_b200.smoke import run_smoke
     run_smoke()
+
+
+def test_cuda_graphed_cfg_pair_equals_eager(small_net):
+    """the CFG-pair forward served from a CUDA graph (one per shape) == the eager call, bit for bit, across replays with new
+    inputs and for a second chunk shape"""
+    from star_b200.video_to_video.cuda_graph import GraphedCFGPair
+    g = GraphedCFGPair(small_net)
+    for seed, (F, H, W) in ((9, (4, 18, 16)), (11, (4, 18, 16)), (12, (5, 18, 16)), (13, (4, 18, 16))):
+        x, hint, y = make_inputs(seed, 1, F, H, W)
+        _, _, ny = make_inputs(seed + 100, 1, F, H, W)
+        t = torch.tensor([100 + 50 * seed]).cuda()
+        want = small_net.forward_cfg_pair(x.cuda(), t, (y.cuda(), ny.cuda()), hint=hint.cuda())
+        got = g.forward_cfg_pair(x.cuda(), t, (y.cuda(), ny.cuda()), hint_chunk=hint.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    assert len(g._graphs) == 2 and g.replays == 4
+
+
+def test_denoise_latents_with_cuda_graph(small_net):
+    """VideoToVideo_sr(cuda_graph=True).denoise_latents == the eager pipeline (chunked clip: two chunk shapes, 3 steps)"""
+    from types import SimpleNamespace
+    from star_b200.video_to_video.video_to_video_model import VideoToVideo_sr
+    feat = torch.randn(1, 4, 12, 18, 16, generator=torch.Generator().manual_seed(3))
+    y, ny = torch.randn(1, 77, 1024, generator=torch.Generator().manual_seed(4)), torch.zeros(1, 77, 1024)
+    outs = []
+    for graphed in (False, True):
+        m = VideoToVideo_sr(SimpleNamespace(model_path=None), device=torch.device("cuda:0"), text_encoder=lambda s: ny, vae=object(),
+                            generator=small_net, cuda_graph=graphed)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        outs.append(m.denoise_latents(feat, y, ny, steps=3, solver_mode="normal", max_chunk_len=8,
+                                      noise=torch.randn(feat.shape, generator=torch.Generator().manual_seed(6)).cuda(),
+                                      noise_sampler=lambda a, b: torch.randn(feat.shape, device="cuda", generator=g)))
+        if graphed:
+            assert m._graphed is not None and m._graphed.replays > 0
+    assert torch.equal(outs[0], outs[1])
