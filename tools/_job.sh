@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --workload cogvideox --gpus 2 --steps 3 --warmup 1 > gpurun_out/k8_bench_cogvideox_n2.json 2> gpurun_out/k8_bench_cogvideox_n2.err
-tail -c 1200 gpurun_out/k8_bench_cogvideox_n2.json; tail -5 gpurun_out/k8_bench_cogvideox_n2.err
+(timeout 600 python -m pytest -m gpu -x -q tests/test_unet_gpu.py -k "graph or cfg_pair" > gpurun_out/k9_tests_graph.log 2>&1; echo "EXIT $?" >> gpurun_out/k9_tests_graph.log); tail -15 gpurun_out/k9_tests_graph.log
+timeout 600 python tools/graph_bench.py > gpurun_out/k9_graph_bench.log 2>&1; tail -12 gpurun_out/k9_graph_bench.log
