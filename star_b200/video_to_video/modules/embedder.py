@@ -9,7 +9,9 @@ the residual in its epilogue -> LayerNorm -> c_fc GEMM with the erf-GELU in its 
 What still comes from the un-vendored ``open_clip`` package (open-clip-torch==2.20.0, requirements.txt:9) is data, not
 arithmetic: the pretrained weights (``create_model_and_transforms``) and the BPE tokenizer with its vocabulary file
 (``open_clip.tokenize``).  Without the package, pass ``state_dict=`` (the CLIP text-side tensors, open_clip key names) and
-``tokenizer=`` (str -> LongTensor (B, 77)) instead; the bench and the parity tests feed text embeddings directly.
+``tokenizer=`` (str -> LongTensor (B, 77)) instead -- or ``weights_path=`` (a local open_clip_pytorch_model.bin) and ``bpe_path=``
+(the package's bpe_simple_vocab_16e6.txt.gz, read by ``clip_tokenizer.SimpleTokenizer``): then nothing of open_clip is imported.
+The bench and the parity tests feed text embeddings directly.
 """
 import torch
 import torch.nn as nn
@@ -105,9 +107,19 @@ class FrozenOpenCLIPEmbedder(nn.Module):
     LAYERS = ["last", "penultimate"]
 
     def __init__(self, pretrained="laion2b_s32b_b79k", arch="ViT-H-14", device="cuda", max_length=77,
-                 freeze=True, layer="penultimate", state_dict=None, tokenizer=None):
+                 freeze=True, layer="penultimate", state_dict=None, tokenizer=None, weights_path=None, bpe_path=None):
         super().__init__()
         assert layer in self.LAYERS
+        if weights_path is not None and state_dict is None:           # a local open_clip_pytorch_model.bin / .safetensors
+            if str(weights_path).endswith(".safetensors"):
+                from safetensors.torch import load_file
+                state_dict = load_file(weights_path)
+            else:
+                state_dict = torch.load(weights_path, map_location="cpu")
+            state_dict = state_dict.get("state_dict", state_dict)
+        if bpe_path is not None and tokenizer is None:                # open_clip's bpe_simple_vocab_16e6.txt.gz
+            from .clip_tokenizer import SimpleTokenizer
+            tokenizer = SimpleTokenizer(bpe_path, context_length=max_length)
         if state_dict is None or tokenizer is None:
             try:
                 import open_clip

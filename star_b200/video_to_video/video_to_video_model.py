@@ -78,7 +78,11 @@ class VideoToVideo_sr():
 
         if text_encoder is None:
             from .modules.embedder import FrozenOpenCLIPEmbedder
-            text_encoder = FrozenOpenCLIPEmbedder(device=self.device, pretrained="laion2b_s32b_b79k")
+            # local files instead of the open_clip package when the options name them (weights: open_clip_pytorch_model.bin of
+            # laion/CLIP-ViT-H-14-laion2B-s32B-b79K, merges: open_clip's bpe_simple_vocab_16e6.txt.gz)
+            text_encoder = FrozenOpenCLIPEmbedder(device=self.device, pretrained="laion2b_s32b_b79k",
+                                                  weights_path=getattr(opt, "clip_weights_path", None),
+                                                  bpe_path=getattr(opt, "clip_bpe_path", None))
             text_encoder.model.to(self.device)
             logger.info('Build encoder with FrozenOpenCLIPEmbedder')
         self.text_encoder = text_encoder

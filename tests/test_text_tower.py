@@ -80,3 +80,48 @@ def test_text_tower_gpu_full_width():
     err = rel_l2(got, want)
     print(f"[text tower] rel-L2 vs fp32 restatement (unpinned) {err:.2e}")
     assert got.shape == (2, 77, 1024) and torch.isfinite(got).all() and err < 4e-3
+
+
+def test_bpe_tokenizer_mechanics(tmp_path):
+    """CLIP's byte-level BPE on a synthetic merge list: merge order by rank, end-of-word marker, lower-casing / whitespace cleaning,
+    <start_of_text> / <end_of_text>, zero padding and truncation to the context length"""
+    import gzip
+    from star_b200.video_to_video.modules.clip_tokenizer import SimpleTokenizer, bytes_to_unicode
+    merges = ["#version: synthetic", "c a", "ca t</w>", "d o", "do g</w>", "t h", "th e</w>"]
+    path = tmp_path / "bpe.txt.gz"
+    with gzip.open(path, "wb") as f:
+        f.write("\n".join(merges).encode())
+    tok = SimpleTokenizer(str(path), context_length=8)
+    assert len(bytes_to_unicode()) == 256 and len(set(bytes_to_unicode().values())) == 256
+    base = 512                                                     # 256 byte symbols + 256 end-of-word variants, then the merges
+    assert tok.encoder["ca"] == base and tok.encoder["cat</w>"] == base + 1 and tok.encoder["the</w>"] == base + 5
+    assert tok.sot == base + 6 and tok.eot == base + 7
+    ids = tok("  The   CAT &amp; dog ")                            # cleaned: "the cat & dog"
+    amp = tok.encoder["&</w>"]
+    assert ids.shape == (1, 8) and ids.dtype == torch.long
+    assert ids[0].tolist() == [tok.sot, base + 5, base + 1, amp, base + 3, tok.eot, 0, 0]
+    assert tok.encode("cats") == [base, tok.encoder["t"], tok.encoder["s</w>"]]      # 'ca' merges, 't s</w>' has no rule
+    long = tok(["cat " * 20, "dog"])
+    assert long.shape == (2, 8) and long[0, 0] == tok.sot and long[0, -1] == tok.eot and (long[0, 1:-1] == base + 1).all()
+    assert long[1].tolist() == [tok.sot, base + 3, tok.eot, 0, 0, 0, 0, 0]
+
+
+def test_embedder_without_open_clip(tmp_path, monkeypatch):
+    """FrozenOpenCLIPEmbedder from a local weight file + merge list: nothing of open_clip is imported"""
+    import builtins
+    import gzip
+    from oracle.open_clip_text_ref import encode_with_transformer, text_manifest
+    from star_b200.utils.synth import synth_state_dict
+    from star_b200.video_to_video.modules.embedder import FrozenOpenCLIPEmbedder
+    _patch(monkeypatch)
+    real_import = builtins.__import__
+    monkeypatch.setattr(builtins, "__import__", lambda name, *a, **k: (_ for _ in ()).throw(ImportError(name))
+                        if name == "open_clip" else real_import(name, *a, **k))
+    sd = synth_state_dict(text_manifest(128, 3, vocab=520), seed=8)
+    torch.save({"state_dict": sd}, tmp_path / "w.bin")
+    with gzip.open(tmp_path / "bpe.txt.gz", "wb") as f:
+        f.write(b"#v\nc a\nca t</w>\nd o\ndo g</w>\nt h\nth e</w>")
+    emb = FrozenOpenCLIPEmbedder(device="cpu", weights_path=str(tmp_path / "w.bin"), bpe_path=str(tmp_path / "bpe.txt.gz"))
+    got = emb.encode(["the cat", "dog"])
+    want = encode_with_transformer(sd, emb._tokenize(["the cat", "dog"]), heads=2, skip_last=1)
+    assert got.shape == (2, 77, 128) and rel_l2(got, want) < 3e-3
