@@ -20,6 +20,8 @@ def sample_sr(network, decoder, cond, uc, lq_latent=None, lq=None, encoder=None,
     if seed is not None:
         torch.manual_seed(seed)
     if lq_latent is None:
+        if lq is None or encoder is None:
+            raise ValueError("sample_sr needs either lq_latent or (lq, encoder)")
         _, F, _, H, W = lq.shape
         shape, dev = (1, (F - 1) // 4 + 1, 16, H // 8, W // 8), lq.device
     else:
