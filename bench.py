@@ -202,17 +202,35 @@ def cpu_sample_setup(kw):
 
 
 def cpu_step_fn(sd, kw, sample):
-    from oracle.unet_ref import UNetCfg, controlled_unet_forward
+    """(step(), kind): one solver step of the reference path on the host cores.  kind "reference" = the reference's OWN, unmodified
+    modules (oracle/ref_loader: /root/reference in the build container, the staged oracle/_ref on a GPU box); kind "port" = the
+    pinned CPU restatement oracle/unet_ref.py (reduced debug model, or no reference tree on this machine)."""
     fs, H, W = sample
     feat, y, ny = synth_inputs(fs, H, W, seed=1)
     x = torch.randn(1, 4, fs, H, W)
     t = torch.tensor([899])
+    net = None
+    if not kw:
+        try:
+            from oracle.ref_loader import build_reference_unet, reference_available
+            if reference_available():
+                net = build_reference_unet(state_dict=sd)
+        except Exception:
+            net = None
+    if net is not None:
+        def step():                  # diffusion_sdedit.py:81,88-97: two model calls + guidance combine
+            with torch.no_grad():
+                a = net(x, t, y, hint=feat)
+                b = net(x, t, ny, hint=feat)
+                return b + 7.5 * (a - b)
+        return step, "reference"
+    from oracle.unet_ref import UNetCfg, controlled_unet_forward
 
     def step():                      # one solver step on the sample: 2 CFG forwards + guidance combine
         a = controlled_unet_forward(sd, x, t, y, feat, UNetCfg(**kw))
         b = controlled_unet_forward(sd, x, t, ny, feat, UNetCfg(**kw))
         return b + 7.5 * (a - b)
-    return step
+    return step, "port"
 
 
 def cpu_extrapolate(dt_step, kw, sample, H, W):
@@ -228,14 +246,15 @@ def cpu_extrapolate(dt_step, kw, sample, H, W):
 
 
 def run_reference(args):
-    """--impl reference: the reference path on the host CPU (oracle port, pinned to the real reference)."""
+    """--impl reference: the reference path on the host CPU -- the reference's own unmodified modules when its tree is on this
+    machine (staged oracle/_ref), else the pinned oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(cpu_threads())
     kw = dict(dim_mult=[1, 2, 1, 4], num_res_blocks=1) if args.small else {}
     sd = cpu_sample_setup(kw)
-    step = cpu_step_fn(sd, kw, CPU_SAMPLE)
+    step, kind = cpu_step_fn(sd, kw, CPU_SAMPLE)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -251,8 +270,9 @@ def run_reference(args):
                                "50 steps, CFG 7.5",
                    "model": "ControlledV2VUNet" + (" (reduced)" if args.small else " 2.04B params"),
                    "parallelism": "cpu", "step": "one solver step (2 CFG forwards) on the bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": note},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": note + ("; the reference's unmodified unet_v2v.py modules (fp32)" if kind == "reference"
+                                           else "; oracle/unet_ref.py, the pinned restatement")},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
